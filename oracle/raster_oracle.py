@@ -1,0 +1,139 @@
+"""ctypes front-end of the CPU rasterizer oracle (oracle/gpsg_oracle.c).
+
+TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and the
+cpu_baseline / `--impl reference` legs of bench.py may import this module.
+
+The oracle restates SURVEY.md Appendix A (the published algorithm of
+graphdeco-inria/diff-gaussian-rasterization, pre-antialiasing API, which the reference calls at
+gaussian_renderer/__init__.py:36-62 and which is absent from /root/reference).
+PARITY UNPINNED against the real extension -- see the header of gpsg_oracle.c.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {}
+
+
+def _lib(tag):
+    if tag not in _LIBS:
+        path = os.path.join(_HERE, "_build", f"liboracle_{tag}.so")
+        if not os.path.exists(path):
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("_oracle_build", os.path.join(_HERE, "build.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        _LIBS[tag] = C.CDLL(path)
+    return _LIBS[tag]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class RasterOracle:
+    """dtype 'f32' (fixed-op-order fp32, for bit-exact integer parity) or 'f64' (gradient truth)."""
+
+    def __init__(self, dtype="f32"):
+        assert dtype in ("f32", "f64")
+        self.tag = dtype
+        self.np = np.float32 if dtype == "f32" else np.float64
+        self.creal = C.c_float if dtype == "f32" else C.c_double
+        self.lib = _lib(dtype)
+
+    def _fn(self, name):
+        return getattr(self.lib, f"{name}_{self.tag}")
+
+    def _a(self, x, shape=None):
+        if x is None:
+            return None
+        x = np.ascontiguousarray(np.asarray(x, dtype=self.np))
+        if shape is not None:
+            x = x.reshape(shape)
+        return x
+
+    def max_threads(self):
+        return int(self._fn("oracle_max_threads")())
+
+    def forward(self, means3D, colors, opacity, scales, rots, view, proj, tanfovx, tanfovy, W, H, bg,
+                scale_mod=1.0, cov3D_precomp=None, nthreads=1, render=True):
+        """view/proj: the 4x4 tensors exactly as the reference passes them (row-vector convention,
+        i.e. flat[c*4+r] = maths M(r,c)); flattened row-major here."""
+        P = int(np.asarray(means3D).reshape(-1, 3).shape[0])
+        r = self.np
+        m3 = self._a(means3D, (P, 3)); col = self._a(colors, (P, 3)); op = self._a(opacity, (P,))
+        sc = self._a(scales, (P, 3)) if scales is not None else None
+        ro = self._a(rots, (P, 4)) if rots is not None else None
+        cp = self._a(cov3D_precomp, (P, 6)) if cov3D_precomp is not None else None
+        vm = self._a(view, (16,)); pm = self._a(proj, (16,)); bgc = self._a(bg, (3,))
+        st = dict(P=P, W=W, H=H)
+        st["radii"] = np.zeros(P, np.int32); st["means2D"] = np.zeros((P, 2), r); st["depth"] = np.zeros(P, r)
+        st["cov3D"] = np.zeros((P, 6), r); st["conic_opacity"] = np.zeros((P, 4), r)
+        st["tiles_touched"] = np.zeros(P, np.uint32); st["rects"] = np.zeros((P, 4), np.int32)
+        f = self._fn("oracle_preprocess"); f.restype = C.c_int
+        cr = self.creal
+        st["n_visible"] = f(C.c_int(P), C.c_int(W), C.c_int(H), _p(m3), _p(sc), _p(ro), _p(op), _p(cp), cr(scale_mod),
+                            _p(vm), _p(pm), cr(tanfovx), cr(tanfovy), _p(st["radii"]), _p(st["means2D"]),
+                            _p(st["depth"]), _p(st["cov3D"]), _p(st["conic_opacity"]), _p(st["tiles_touched"]),
+                            _p(st["rects"]))
+        N = int(st["tiles_touched"].astype(np.int64).sum())
+        gx, gy = (W + 15) // 16, (H + 15) // 16
+        st["keys"] = np.zeros(max(N, 1), np.uint64)[:N]; st["vals"] = np.zeros(max(N, 1), np.uint32)[:N]
+        st["ranges"] = np.zeros((gx * gy, 2), np.uint32)
+        depth32 = np.ascontiguousarray(st["depth"].astype(np.float32))
+        keys = np.zeros(max(N, 1), np.uint64); vals = np.zeros(max(N, 1), np.uint32)
+        f = self._fn("oracle_bin"); f.restype = C.c_int64
+        n = f(C.c_int(P), C.c_int(W), C.c_int(H), _p(st["radii"]), _p(st["rects"]), _p(depth32), _p(keys), _p(vals),
+              _p(st["ranges"]))
+        assert n == N, (n, N)
+        st["keys"], st["vals"], st["num_rendered"] = keys[:N], vals[:N], N
+        st["_vals_full"] = vals
+        st["inputs"] = dict(means3D=m3, colors=col, opacity=op, scales=sc, rots=ro, cov3D_precomp=cp, view=vm, proj=pm,
+                            tanfovx=tanfovx, tanfovy=tanfovy, bg=bgc, scale_mod=scale_mod)
+        if render:
+            st["color"] = np.zeros((3, H, W), r); st["final_T"] = np.zeros((H, W), r)
+            st["n_contrib"] = np.zeros((H, W), np.uint32)
+            self._fn("oracle_render")(C.c_int(W), C.c_int(H), _p(st["ranges"]), _p(vals), _p(st["means2D"]), _p(col),
+                                      _p(st["conic_opacity"]), _p(bgc), _p(st["color"]), _p(st["final_T"]),
+                                      _p(st["n_contrib"]), C.c_int(nthreads))
+        return st
+
+    def backward(self, st, dL_dpix):
+        P, W, H = st["P"], st["W"], st["H"]
+        r = self.np
+        i = st["inputs"]
+        g = self._a(dL_dpix, (3, H, W))
+        out = dict(dL_dmean2D=np.zeros((P, 2), r), dL_dconic=np.zeros((P, 3), r), dL_dopacity=np.zeros(P, r),
+                   dL_dcolors=np.zeros((P, 3), r), dL_dmeans3D=np.zeros((P, 3), r), dL_dcov3D=np.zeros((P, 6), r),
+                   dL_dscales=np.zeros((P, 3), r), dL_drots=np.zeros((P, 4), r))
+        self._fn("oracle_render_backward")(C.c_int(P), C.c_int(W), C.c_int(H), _p(st["ranges"]), _p(st["_vals_full"]),
+                                           _p(st["means2D"]), _p(i["colors"]), _p(st["conic_opacity"]), _p(i["bg"]),
+                                           _p(st["final_T"]), _p(st["n_contrib"]), _p(g), _p(out["dL_dmean2D"]),
+                                           _p(out["dL_dconic"]), _p(out["dL_dopacity"]), _p(out["dL_dcolors"]))
+        cr = self.creal
+        self._fn("oracle_preprocess_backward")(C.c_int(P), C.c_int(W), C.c_int(H), _p(i["means3D"]), _p(st["radii"]),
+                                               _p(i["scales"]), _p(i["rots"]), _p(i["cov3D_precomp"]), cr(i["scale_mod"]),
+                                               _p(i["view"]), _p(i["proj"]), cr(i["tanfovx"]), cr(i["tanfovy"]),
+                                               _p(out["dL_dmean2D"]), _p(out["dL_dconic"]), _p(out["dL_dmeans3D"]),
+                                               _p(out["dL_dcov3D"]), _p(out["dL_dscales"]), _p(out["dL_drots"]))
+        return out
+
+    def mark_visible(self, means3D, view):
+        P = int(np.asarray(means3D).reshape(-1, 3).shape[0])
+        m3 = self._a(means3D, (P, 3)); vm = self._a(view, (16,))
+        out = np.zeros(P, np.uint8)
+        self._fn("oracle_mark_visible")(C.c_int(P), _p(m3), _p(vm), _p(out))
+        return out.astype(bool)
+
+
+def taichi_splat(pts, mask, res, dtype="f32"):
+    """Restated reference lib/TaichiRender.py:12-23 (one call = one view's points). Returns (depth, color)."""
+    o = RasterOracle(dtype)
+    pts = o._a(pts); B, N = pts.shape[0], pts.shape[1]
+    mask = o._a(mask, (B, N))
+    depth = np.zeros((B, 1, res, res), o.np); color = np.full((B, 3, res, res), -1.0, o.np)
+    o._fn("oracle_taichi_splat")(C.c_int(B), C.c_int(N), C.c_int(res), _p(pts), _p(mask), _p(depth), _p(color))
+    return depth, color
