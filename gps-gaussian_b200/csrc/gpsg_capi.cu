@@ -1,0 +1,365 @@
+// gpsg_capi.cu -- the extern "C" boundary of libgpsg_sm100.so (declared in include/gpsg.h).
+// Host-side orchestration only; kernels live in raster_*.cu / corr.cu.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "gpsg_internal.cuh"
+
+namespace gpsg {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+Camera make_camera(const GpsgRasterSettings& s) {
+    Camera c;
+    memcpy(c.view, s.viewmatrix, sizeof(c.view));
+    memcpy(c.proj, s.projmatrix, sizeof(c.proj));
+    c.tanfovx = s.tanfovx;
+    c.tanfovy = s.tanfovy;
+    c.W = s.image_width;
+    c.H = s.image_height;
+    c.focal_x = (float)c.W / (2.0f * s.tanfovx);
+    c.focal_y = (float)c.H / (2.0f * s.tanfovy);
+    c.scale_modifier = s.scale_modifier;
+    c.grid_x = (c.W + GPSG_TILE_X - 1) / GPSG_TILE_X;
+    c.grid_y = (c.H + GPSG_TILE_Y - 1) / GPSG_TILE_Y;
+    for (int k = 0; k < 3; ++k) { c.bg[k] = s.bg[k]; c.campos[k] = s.campos[k]; }
+    return c;
+}
+
+// ---- buffer layouts -------------------------------------------------------------------------
+template <typename T>
+static inline T* take(char*& p, size_t count) {
+    T* r = reinterpret_cast<T*>(p);
+    p += align_up(count * sizeof(T));
+    return r;
+}
+
+static GeomState carve_geom(char* p, int P, size_t scan_bytes, char** end) {
+    GeomState g;
+    const size_t n = (size_t)(P > 0 ? P : 1);
+    g.depths = take<float>(p, n);
+    g.means2D = take<float2>(p, n);
+    g.conic_opacity = take<float4>(p, n);
+    g.rgb = take<float>(p, 3 * n);
+    g.clamped = take<uint8_t>(p, 3 * n);
+    g.tiles_touched = take<uint32_t>(p, n);
+    g.point_offsets = take<uint32_t>(p, n);
+    g.scan_temp = p;
+    g.scan_temp_bytes = scan_bytes;
+    p += align_up(scan_bytes);
+    if (end) *end = p;
+    return g;
+}
+size_t GeomState::required(int P, size_t scan_bytes) {
+    char* end = nullptr;
+    carve_geom(nullptr, P, scan_bytes, &end);
+    return (size_t)(end - (char*)nullptr) + 256;
+}
+GeomState GeomState::carve(void* base, int P, size_t scan_bytes) {
+    return carve_geom((char*)align_up((size_t)base), P, scan_bytes, nullptr);
+}
+
+static BinningState carve_binning(char* p, size_t N, size_t sort_bytes, char** end) {
+    BinningState b;
+    const size_t n = N > 0 ? N : 1;
+    b.slabA = take<float4>(p, n);
+    b.slabB = take<float4>(p, n);
+    b.slabC = take<float4>(p, n);
+    b.keys = take<uint64_t>(p, n);
+    b.vals = take<uint32_t>(p, n);
+    b.keys_unsorted = take<uint64_t>(p, n);
+    b.vals_unsorted = take<uint32_t>(p, n);
+    b.sort_temp = p;
+    b.sort_temp_bytes = sort_bytes;
+    p += align_up(sort_bytes);
+    if (end) *end = p;
+    return b;
+}
+size_t BinningState::required(size_t N, size_t sort_bytes) {
+    char* end = nullptr;
+    carve_binning(nullptr, N, sort_bytes, &end);
+    return (size_t)(end - (char*)nullptr) + 256;
+}
+BinningState BinningState::carve(void* base, size_t N, size_t sort_bytes) {
+    return carve_binning((char*)align_up((size_t)base), N, sort_bytes, nullptr);
+}
+
+static ImageState carve_image(char* p, int W, int H, char** end) {
+    ImageState im;
+    const size_t hw = (size_t)W * H;
+    const size_t tiles = (size_t)((W + GPSG_TILE_X - 1) / GPSG_TILE_X) * ((H + GPSG_TILE_Y - 1) / GPSG_TILE_Y);
+    im.final_T = take<float>(p, hw > 0 ? hw : 1);
+    im.n_contrib = take<uint32_t>(p, hw > 0 ? hw : 1);
+    im.ranges = take<uint2>(p, tiles > 0 ? tiles : 1);
+    if (end) *end = p;
+    return im;
+}
+size_t ImageState::required(int W, int H) {
+    char* end = nullptr;
+    carve_image(nullptr, W, H, &end);
+    return (size_t)(end - (char*)nullptr) + 256;
+}
+ImageState ImageState::carve(void* base, int W, int H) { return carve_image((char*)align_up((size_t)base), W, H, nullptr); }
+
+static int bit_length(uint32_t n) {
+    int b = 0;
+    while (n) { ++b; n >>= 1; }
+    return b;
+}
+
+// pinned host slot for the one device->host read of the forward (num_rendered)
+static uint32_t* pinned_slot() {
+    static thread_local uint32_t* slot = nullptr;
+    if (!slot) {
+        if (cudaHostAlloc((void**)&slot, 64, cudaHostAllocDefault) != cudaSuccess) slot = nullptr;
+    }
+    return slot;
+}
+
+}  // namespace gpsg
+
+
+// ---- profiling -------------------------------------------------------------------------------
+#include <vector>
+namespace gpsg {
+struct ProfSlot { cudaEvent_t a, b; Stage stage; bool used; };
+struct Profiler {
+    bool on = false;
+    std::vector<ProfSlot> slots;
+    size_t next = 0;
+    int launches[ST_COUNT] = {0};
+};
+static thread_local Profiler g_prof;
+static const char* kStageNames[ST_COUNT] = {"preprocess", "scan", "duplicate", "sort", "gather_ranges", "render_forward",
+                                            "render_backward", "preprocess_backward", "corr_forward", "corr_backward"};
+StageTimer::StageTimer(Stage s, cudaStream_t st, int launches) : stage(s), stream(st), slot(nullptr) {
+    if (!g_prof.on) return;
+    if (g_prof.next == g_prof.slots.size()) {
+        ProfSlot ps; ps.used = false;
+        if (cudaEventCreate(&ps.a) != cudaSuccess || cudaEventCreate(&ps.b) != cudaSuccess) return;
+        g_prof.slots.push_back(ps);
+    }
+    ProfSlot* p = &g_prof.slots[g_prof.next++];
+    p->stage = s; p->used = true;
+    g_prof.launches[s] += launches;
+    cudaEventRecord(p->a, stream);
+    slot = (void*)(uintptr_t)(g_prof.next);  // index+1 (vector may reallocate)
+}
+StageTimer::~StageTimer() {
+    if (!slot) return;
+    cudaEventRecord(g_prof.slots[(size_t)(uintptr_t)slot - 1].b, stream);
+}
+}  // namespace gpsg
+
+using namespace gpsg;
+
+extern "C" {
+
+GPSG_API const char* gpsg_last_error(void) { return g_err; }
+int gpsg_version(void) { return 100; }
+
+int gpsg_rasterize_forward(const GpsgRasterSettings* s, int device, void* stream_, int P, int sh_M,
+                           const float* means3D, const float* colors_precomp, const float* shs,
+                           const float* opacities, const float* scales, const float* rotations,
+                           const float* cov3D_precomp, float* out_color, int32_t* radii, gpsg_alloc_fn geom_alloc,
+                           void* geom_user, gpsg_alloc_fn binning_alloc, void* binning_user,
+                           gpsg_alloc_fn image_alloc, void* image_user, int32_t* num_rendered) {
+    GPSG_REQUIRE(s != nullptr, "settings is NULL");
+    GPSG_REQUIRE(P >= 0, "P < 0");
+    GPSG_REQUIRE(s->image_width > 0 && s->image_height > 0, "image size must be positive");
+    GPSG_REQUIRE(out_color != nullptr, "out_color is NULL");
+    GPSG_REQUIRE(geom_alloc && binning_alloc && image_alloc, "allocator callback is NULL");
+    if (P > 0) {
+        GPSG_REQUIRE(means3D && opacities && radii, "means3D / opacities / radii is NULL");
+        GPSG_REQUIRE((colors_precomp != nullptr) != (shs != nullptr),
+                     "Please provide excatly one of either SHs or precomputed colors!");
+        GPSG_REQUIRE(((scales != nullptr && rotations != nullptr) != (cov3D_precomp != nullptr)),
+                     "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+        GPSG_REQUIRE(shs == nullptr, "SH colour path is not built yet (GPS-Gaussian passes colors_precomp)");
+    }
+    (void)sh_M;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GPSG_CUDA(cudaSetDevice(device));
+    const Camera cam = make_camera(*s);
+
+    const size_t scan_bytes = scan_temp_bytes(P);
+    void* geom_base = geom_alloc(geom_user, GeomState::required(P, scan_bytes));
+    if (!geom_base) { set_error("geometry allocator returned NULL"); return GPSG_E_ALLOC; }
+    GeomState g = GeomState::carve(geom_base, P, scan_bytes);
+
+    uint32_t N = 0;
+    if (P > 0) {
+        int rc;
+        { StageTimer t(ST_PREPROCESS, stream, 1); rc = launch_preprocess(cam, P, means3D, scales, rotations, opacities, cov3D_precomp, radii, g, stream); }
+        if (rc) return rc;
+        { StageTimer t(ST_SCAN, stream, 2); rc = run_scan(g, P, stream); }
+        if (rc) return rc;
+        uint32_t* slot = pinned_slot();
+        GPSG_REQUIRE(slot != nullptr, "cudaHostAlloc failed");
+        GPSG_CUDA(cudaMemcpyAsync(slot, g.point_offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        GPSG_CUDA(cudaStreamSynchronize(stream));
+        N = *slot;
+    }
+    if (num_rendered) *num_rendered = (int32_t)N;
+
+    const int end_bit = 32 + bit_length((uint32_t)(cam.grid_x * cam.grid_y));
+    const size_t sort_bytes = sort_temp_bytes(N, end_bit);
+    void* bin_base = binning_alloc(binning_user, BinningState::required(N, sort_bytes));
+    if (!bin_base) { set_error("binning allocator returned NULL"); return GPSG_E_ALLOC; }
+    BinningState b = BinningState::carve(bin_base, N, sort_bytes);
+    void* img_base = image_alloc(image_user, ImageState::required(cam.W, cam.H));
+    if (!img_base) { set_error("image allocator returned NULL"); return GPSG_E_ALLOC; }
+    ImageState im = ImageState::carve(img_base, cam.W, cam.H);
+
+    int rc = GPSG_OK;
+    if (N > 0) {
+        { StageTimer t(ST_DUPLICATE, stream, 1); rc = launch_duplicate(cam, P, radii, g, b, stream); }
+        if (rc) return rc;
+        { StageTimer t(ST_SORT, stream, 2 + (end_bit + 7) / 8); rc = run_sort(b, N, end_bit, stream); }
+        if (rc) return rc;
+    }
+    { StageTimer t(ST_GATHER, stream, N > 0 ? 1 : 0); rc = launch_gather_ranges(cam, N, colors_precomp, g, b, im, stream); }
+    if (rc) return rc;
+    { StageTimer t(ST_RENDER_FWD, stream, 1); rc = launch_render_forward(cam, b, im, out_color, stream); }
+    if (rc) return rc;
+    if (s->debug) GPSG_CUDA(cudaStreamSynchronize(stream));
+    return GPSG_OK;
+}
+
+size_t gpsg_rasterize_backward_workspace_bytes(int P) { return align_up(sizeof(float4) * (size_t)(P > 0 ? P : 1)) + 256; }
+
+int gpsg_rasterize_backward(const GpsgRasterSettings* s, int device, void* stream_, int P, int sh_M,
+                            int32_t num_rendered, const float* means3D, const float* colors_precomp, const float* shs,
+                            const float* opacities, const float* scales, const float* rotations,
+                            const float* cov3D_precomp, const int32_t* radii, const void* geom_buffer,
+                            const void* binning_buffer, const void* image_buffer, const float* dL_dout_color,
+                            float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D,
+                            float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drotations,
+                            void* workspace) {
+    GPSG_REQUIRE(s != nullptr, "settings is NULL");
+    GPSG_REQUIRE(P >= 0 && num_rendered >= 0, "negative size");
+    if (P == 0) return GPSG_OK;
+    GPSG_REQUIRE(means3D && radii && geom_buffer && binning_buffer && image_buffer && dL_dout_color,
+                 "a required input pointer is NULL");
+    GPSG_REQUIRE(dL_dmeans2D && dL_dcolors && dL_dopacity && dL_dmeans3D && workspace,
+                 "a required output pointer is NULL");
+    GPSG_REQUIRE(shs == nullptr && dL_dsh == nullptr, "SH colour path is not built yet");
+    GPSG_REQUIRE((scales && rotations) || cov3D_precomp, "need scales+rotations or cov3D_precomp");
+    (void)sh_M; (void)colors_precomp; (void)opacities;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GPSG_CUDA(cudaSetDevice(device));
+    const Camera cam = make_camera(*s);
+    BinningState b = BinningState::carve(const_cast<void*>(binning_buffer), (size_t)num_rendered, 0);
+    ImageState im = ImageState::carve(const_cast<void*>(image_buffer), cam.W, cam.H);
+    float4* dconic_op = (float4*)align_up((size_t)workspace);
+    GPSG_CUDA(cudaMemsetAsync(dL_dmeans2D, 0, sizeof(float) * 3 * (size_t)P, stream));
+    GPSG_CUDA(cudaMemsetAsync(dL_dcolors, 0, sizeof(float) * 3 * (size_t)P, stream));
+    GPSG_CUDA(cudaMemsetAsync(dconic_op, 0, sizeof(float4) * (size_t)P, stream));
+    int rc = GPSG_OK;
+    if (num_rendered > 0) {
+        { StageTimer t(ST_RENDER_BWD, stream, 1); rc = launch_render_backward(cam, b, im, dL_dout_color, dL_dmeans2D, dconic_op, dL_dcolors, stream); }
+        if (rc) return rc;
+    }
+    { StageTimer t(ST_PREPROCESS_BWD, stream, 1);
+    rc = launch_preprocess_backward(cam, P, means3D, radii, cov3D_precomp ? nullptr : scales,
+                                    cov3D_precomp ? nullptr : rotations, cov3D_precomp, dL_dmeans2D, dconic_op,
+                                    dL_dopacity, dL_dmeans3D, dL_dcov3D, cov3D_precomp ? nullptr : dL_dscales,
+                                    cov3D_precomp ? nullptr : dL_drotations, stream); }
+    if (rc) return rc;
+    if (cov3D_precomp) {
+        if (dL_dscales) GPSG_CUDA(cudaMemsetAsync(dL_dscales, 0, sizeof(float) * 3 * (size_t)P, stream));
+        if (dL_drotations) GPSG_CUDA(cudaMemsetAsync(dL_drotations, 0, sizeof(float) * 4 * (size_t)P, stream));
+    }
+    if (s->debug) GPSG_CUDA(cudaStreamSynchronize(stream));
+    return GPSG_OK;
+}
+
+int gpsg_mark_visible(int device, void* stream_, int P, const float* means3D, const float* viewmatrix_host16,
+                      uint8_t* present) {
+    GPSG_REQUIRE(P >= 0, "P < 0");
+    if (P == 0) return GPSG_OK;
+    GPSG_REQUIRE(means3D && viewmatrix_host16 && present, "NULL pointer");
+    GPSG_CUDA(cudaSetDevice(device));
+    return launch_mark_visible(P, means3D, viewmatrix_host16, present, (cudaStream_t)stream_);
+}
+
+int gpsg_geom_view(const void* geom_buffer, int P, GpsgGeomView* out) {
+    GPSG_REQUIRE(geom_buffer && out, "NULL pointer");
+    GeomState g = GeomState::carve(const_cast<void*>(geom_buffer), P, 0);
+    out->depths = g.depths;
+    out->means2D = reinterpret_cast<const float*>(g.means2D);
+    out->conic_opacity = reinterpret_cast<const float*>(g.conic_opacity);
+    out->tiles_touched = g.tiles_touched;
+    out->point_offsets = g.point_offsets;
+    return GPSG_OK;
+}
+int gpsg_binning_view(const void* binning_buffer, int64_t num_rendered, GpsgBinningView* out) {
+    GPSG_REQUIRE(binning_buffer && out && num_rendered >= 0, "bad argument");
+    BinningState b = BinningState::carve(const_cast<void*>(binning_buffer), (size_t)num_rendered, 0);
+    out->point_list_keys = b.keys;
+    out->point_list = b.vals;
+    return GPSG_OK;
+}
+int gpsg_image_view(const void* image_buffer, int W, int H, GpsgImageView* out) {
+    GPSG_REQUIRE(image_buffer && out && W > 0 && H > 0, "bad argument");
+    ImageState im = ImageState::carve(const_cast<void*>(image_buffer), W, H);
+    out->final_T = im.final_T;
+    out->n_contrib = im.n_contrib;
+    out->ranges = reinterpret_cast<const uint32_t*>(im.ranges);
+    return GPSG_OK;
+}
+
+int gpsg_corr_sampler_forward(int device, void* stream_, int dtype, int B, int H, int W1, int W2, const void* volume,
+                              int64_t sb, int64_t sh, int64_t sw1, const float* coords, int64_t coords_sb, int radius,
+                              void* out) {
+    GPSG_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp32) or 1 (fp16)");
+    GPSG_REQUIRE(B >= 0 && H >= 0 && W1 >= 0 && W2 >= 0 && radius >= 0 && radius <= 31, "bad shape / radius");
+    if ((int64_t)B * H * W1 == 0) return GPSG_OK;
+    GPSG_REQUIRE(volume && coords && out, "NULL pointer");
+    GPSG_CUDA(cudaSetDevice(device));
+    StageTimer t(ST_CORR_FWD, (cudaStream_t)stream_, 1);
+    return launch_corr_fwd(dtype, B, H, W1, W2, volume, sb, sh, sw1, coords, coords_sb, radius, out,
+                           (cudaStream_t)stream_);
+}
+
+int gpsg_corr_sampler_backward(int device, void* stream_, int dtype, int B, int H, int W1, int W2, const float* coords,
+                               int64_t coords_sb, const void* grad_out, int radius, void* grad_volume) {
+    GPSG_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp32) or 1 (fp16)");
+    GPSG_REQUIRE(B >= 0 && H >= 0 && W1 >= 0 && W2 >= 0 && radius >= 0 && radius <= 31, "bad shape / radius");
+    if ((int64_t)B * H * W1 * W2 == 0) return GPSG_OK;
+    GPSG_REQUIRE(coords && grad_out && grad_volume, "NULL pointer");
+    GPSG_CUDA(cudaSetDevice(device));
+    StageTimer t(ST_CORR_BWD, (cudaStream_t)stream_, 1);
+    return launch_corr_bwd(dtype, B, H, W1, W2, coords, coords_sb, grad_out, radius, grad_volume,
+                           (cudaStream_t)stream_);
+}
+
+
+int gpsg_profile_enable(int on) {
+    g_prof.on = on != 0;
+    return GPSG_OK;
+}
+const char* gpsg_profile_stage_name(int stage) { return (stage >= 0 && stage < ST_COUNT) ? kStageNames[stage] : ""; }
+int gpsg_profile_read(float* total_ms, int32_t* calls, int32_t* launches, int capacity) {
+    GPSG_REQUIRE(total_ms && calls && launches && capacity >= ST_COUNT, "profile_read: capacity < stage count");
+    for (int i = 0; i < ST_COUNT; ++i) { total_ms[i] = 0.f; calls[i] = 0; launches[i] = g_prof.launches[i]; g_prof.launches[i] = 0; }
+    for (size_t k = 0; k < g_prof.next; ++k) {
+        ProfSlot& p = g_prof.slots[k];
+        if (!p.used) continue;
+        GPSG_CUDA(cudaEventSynchronize(p.b));
+        float ms = 0.f;
+        GPSG_CUDA(cudaEventElapsedTime(&ms, p.a, p.b));
+        total_ms[p.stage] += ms; calls[p.stage] += 1; p.used = false;
+    }
+    g_prof.next = 0;
+    return ST_COUNT;
+}
+
+}  // extern "C"

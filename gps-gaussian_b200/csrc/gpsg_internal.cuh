@@ -1,0 +1,123 @@
+// gpsg_internal.cuh -- shared declarations of libgpsg_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/gpsg.h"
+
+#define GPSG_TILE_X 16
+#define GPSG_TILE_Y 16
+#define GPSG_TILE_PIX 256
+
+namespace gpsg {
+
+void set_error(const char* fmt, ...);
+
+#define GPSG_CUDA(expr)                                                                         \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            gpsg::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return GPSG_E_CUDA;                                                                 \
+        }                                                                                       \
+    } while (0)
+#define GPSG_LAUNCH_CHECK() GPSG_CUDA(cudaGetLastError())
+#define GPSG_REQUIRE(cond, msg)                                  \
+    do {                                                         \
+        if (!(cond)) {                                           \
+            gpsg::set_error("%s:%d: %s", __FILE__, __LINE__, msg); \
+            return GPSG_E_INVALID;                               \
+        }                                                        \
+    } while (0)
+
+// Camera block passed by value (__grid_constant__) to kernels.
+struct Camera {
+    float view[16];
+    float proj[16];
+    float tanfovx, tanfovy, focal_x, focal_y;
+    float scale_modifier;
+    int W, H, grid_x, grid_y;
+    float bg[3];
+    float campos[3];
+};
+Camera make_camera(const GpsgRasterSettings& s);
+
+static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// ---- saved-state layouts (carved from the caller-allocated byte buffers) -------------------
+struct GeomState {
+    float* depths;            // [P]
+    float2* means2D;          // [P]
+    float4* conic_opacity;    // [P]
+    float* rgb;               // [P,3]   (SH path only; colours converted from SH)
+    uint8_t* clamped;         // [P,3]   (SH path only)
+    uint32_t* tiles_touched;  // [P]
+    uint32_t* point_offsets;  // [P]
+    void* scan_temp;
+    size_t scan_temp_bytes;
+    static size_t required(int P, size_t scan_temp_bytes);
+    static GeomState carve(void* base, int P, size_t scan_temp_bytes);
+};
+struct BinningState {
+    uint64_t* keys_unsorted;  // [N]
+    uint32_t* vals_unsorted;  // [N]
+    uint64_t* keys;           // [N] sorted (tile<<32 | depth bits)
+    uint32_t* vals;           // [N] sorted Gaussian ids ("point_list")
+    float4* slabA;            // [N] (x, y, conic.x, conic.y)          sorted, tile-contiguous
+    float4* slabB;            // [N] (conic.z, opacity, r, g)
+    float4* slabC;            // [N] (b, id bits, 0, 0)
+    void* sort_temp;
+    size_t sort_temp_bytes;
+    static size_t required(size_t N, size_t sort_temp_bytes);
+    static BinningState carve(void* base, size_t N, size_t sort_temp_bytes);
+};
+struct ImageState {
+    float* final_T;       // [HW]
+    uint32_t* n_contrib;  // [HW]
+    uint2* ranges;        // [tiles]
+    static size_t required(int W, int H);
+    static ImageState carve(void* base, int W, int H);
+};
+size_t scan_temp_bytes(int P);
+size_t sort_temp_bytes(size_t N, int end_bit);
+
+// ---- kernel launchers (each enqueues on `stream`) ------------------------------------------
+// raster_preprocess.cu  (compiled with -fmad=false: integer outputs follow the oracle's op order)
+int launch_preprocess(const Camera& cam, int P, const float* means3D, const float* scales, const float* rots,
+                      const float* opacities, const float* cov3D_precomp, int32_t* radii, GeomState g,
+                      cudaStream_t stream);
+int launch_mark_visible(int P, const float* means3D, const float* view16_host, uint8_t* present, cudaStream_t stream);
+// raster_binning.cu
+int run_scan(GeomState g, int P, cudaStream_t stream);
+int launch_duplicate(const Camera& cam, int P, const int32_t* radii, GeomState g, BinningState b, cudaStream_t stream);
+int run_sort(BinningState b, size_t N, int end_bit, cudaStream_t stream);
+int launch_gather_ranges(const Camera& cam, size_t N, const float* colors, GeomState g, BinningState b, ImageState im,
+                         cudaStream_t stream);
+// raster_render.cu
+int launch_render_forward(const Camera& cam, BinningState b, ImageState im, float* out_color, cudaStream_t stream);
+// raster_backward.cu
+int launch_render_backward(const Camera& cam, BinningState b, ImageState im, const float* dL_dpix,
+                           float* dL_dmeans2D /*[P,3]*/, float4* dL_dconic_op /*[P] (x,y,w,opacity)*/,
+                           float* dL_dcolors /*[P,3]*/, cudaStream_t stream);
+int launch_preprocess_backward(const Camera& cam, int P, const float* means3D, const int32_t* radii,
+                               const float* scales, const float* rots, const float* cov3D_precomp,
+                               const float* dL_dmeans2D, const float4* dL_dconic_op, float* dL_dopacity,
+                               float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales, float* dL_drots,
+                               cudaStream_t stream);
+// corr.cu
+int launch_corr_fwd(int dtype, int B, int H, int W1, int W2, const void* vol, int64_t sb, int64_t sh, int64_t sw1,
+                    const float* coords, int64_t csb, int r, void* out, cudaStream_t stream);
+int launch_corr_bwd(int dtype, int B, int H, int W1, int W2, const float* coords, int64_t csb, const void* gout, int r,
+                    void* gvol, cudaStream_t stream);
+
+
+// ---- optional per-stage timing (bench.py); see gpsg_profile_* in gpsg.h ---------------------
+enum Stage { ST_PREPROCESS = 0, ST_SCAN, ST_DUPLICATE, ST_SORT, ST_GATHER, ST_RENDER_FWD, ST_RENDER_BWD,
+             ST_PREPROCESS_BWD, ST_CORR_FWD, ST_CORR_BWD, ST_COUNT };
+struct StageTimer {  // RAII: records begin/end events on `stream` when profiling is on
+    StageTimer(Stage s, cudaStream_t stream, int launches);
+    ~StageTimer();
+    Stage stage; cudaStream_t stream; void* slot;
+};
+
+}  // namespace gpsg

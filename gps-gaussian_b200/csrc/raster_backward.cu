@@ -1,0 +1,315 @@
+// raster_backward.cu -- backward of the splat rasterizer (upstream
+// backward.cu::renderCUDA / computeCov2DCUDA / preprocessCUDA, reached from
+// _RasterizeGaussians.backward behind reference gaussian_renderer/__init__.py:54-62).
+#include "gpsg_internal.cuh"
+
+namespace gpsg {
+
+__device__ __forceinline__ void tile_pixel_b(int tid, int& lx, int& ly) {
+    const int w = tid >> 5, l = tid & 31;
+    lx = ((w & 1) << 3) + (l & 7);
+    ly = ((w >> 1) << 2) + (l >> 3);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// A.6: per tile, pixels replay their list back to front.  Gradients of one (tile, Gaussian) pair are
+// reduced over the warp with shuffles, then one atomic per component per warp.
+__global__ void __launch_bounds__(256) render_backward_kernel(const __grid_constant__ Camera cam,
+                                                              const float4* __restrict__ slabA,
+                                                              const float4* __restrict__ slabB,
+                                                              const float4* __restrict__ slabC,
+                                                              const uint2* __restrict__ ranges,
+                                                              const float* __restrict__ final_T,
+                                                              const uint32_t* __restrict__ n_contrib,
+                                                              const float* __restrict__ dL_dpix,
+                                                              float* __restrict__ dL_dmeans2D,
+                                                              float4* __restrict__ dL_dconic_op,
+                                                              float* __restrict__ dL_dcolors) {
+    __shared__ float4 sA[GPSG_TILE_PIX];
+    __shared__ float4 sB[GPSG_TILE_PIX];
+    __shared__ float2 sC[GPSG_TILE_PIX];  // (blue, id bits)
+
+    const int tile = blockIdx.y * cam.grid_x + blockIdx.x;
+    int lx, ly;
+    tile_pixel_b(threadIdx.x, lx, ly);
+    const int px = blockIdx.x * GPSG_TILE_X + lx, py = blockIdx.y * GPSG_TILE_Y + ly;
+    const bool inside = px < cam.W && py < cam.H;
+    const float pixfx = (float)px, pixfy = (float)py;
+    const uint2 range = ranges[tile];
+    const int total = (int)(range.y - range.x);
+    const int rounds = (total + GPSG_TILE_PIX - 1) / GPSG_TILE_PIX;
+    const size_t HW = (size_t)cam.W * cam.H;
+    const size_t pid = (size_t)py * cam.W + px;
+
+    const float T_final = inside ? final_T[pid] : 0.0f;
+    float T = T_final;
+    uint32_t contributor = (uint32_t)total;
+    const uint32_t last_contributor = inside ? n_contrib[pid] : 0u;
+    float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f, lastc0 = 0.f, lastc1 = 0.f, lastc2 = 0.f, last_alpha = 0.f;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    if (inside) { g0 = dL_dpix[pid]; g1 = dL_dpix[HW + pid]; g2 = dL_dpix[2 * HW + pid]; }
+    const float bg_dot = (cam.bg[0] * g0 + cam.bg[1] * g1) + cam.bg[2] * g2;
+    const float ddelx_dx = 0.5f * (float)cam.W, ddely_dy = 0.5f * (float)cam.H;
+    // the whole CTA can skip list entries behind the deepest contributor of any pixel
+    int todo = total;
+    for (int r = 0; r < rounds; ++r, todo -= GPSG_TILE_PIX) {
+        __syncthreads();
+        const int n = min(GPSG_TILE_PIX, todo);
+        if ((int)threadIdx.x < n) {
+            const size_t k = (size_t)range.y - 1 - (size_t)r * GPSG_TILE_PIX - threadIdx.x;  // back to front
+            sA[threadIdx.x] = slabA[k];
+            sB[threadIdx.x] = slabB[k];
+            const float4 c = slabC[k];
+            sC[threadIdx.x] = make_float2(c.x, c.y);
+        }
+        __syncthreads();
+        for (int j = 0; j < n; ++j) {
+            --contributor;
+            bool active = inside && contributor < last_contributor;
+            float dL_dmx = 0.f, dL_dmy = 0.f, dL_dcx = 0.f, dL_dcy = 0.f, dL_dcw = 0.f, dL_dop = 0.f;
+            float dL_dr = 0.f, dL_dg = 0.f, dL_db = 0.f;
+            if (active) {
+                const float4 a = sA[j];
+                const float4 b = sB[j];
+                const float dx = a.x - pixfx, dy = a.y - pixfy;
+                const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+                const float G = __expf(power);
+                const float alpha = fminf(0.99f, b.y * G);
+                active = !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                if (active) {
+                    T = T / (1.0f - alpha);
+                    const float dchannel_dcolor = alpha * T;
+                    const float cb = sC[j].x;
+                    float dL_dalpha = 0.f;
+                    accum0 = last_alpha * lastc0 + (1.f - last_alpha) * accum0; lastc0 = b.z;
+                    accum1 = last_alpha * lastc1 + (1.f - last_alpha) * accum1; lastc1 = b.w;
+                    accum2 = last_alpha * lastc2 + (1.f - last_alpha) * accum2; lastc2 = cb;
+                    dL_dalpha += (b.z - accum0) * g0;
+                    dL_dalpha += (b.w - accum1) * g1;
+                    dL_dalpha += (cb - accum2) * g2;
+                    dL_dr = dchannel_dcolor * g0; dL_dg = dchannel_dcolor * g1; dL_db = dchannel_dcolor * g2;
+                    dL_dalpha *= T;
+                    last_alpha = alpha;
+                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                    const float dL_dG = b.y * dL_dalpha;
+                    const float gdx = G * dx, gdy = G * dy;
+                    const float dG_ddelx = -gdx * a.z - gdy * a.w;
+                    const float dG_ddely = -gdy * b.x - gdx * a.w;
+                    dL_dmx = dL_dG * dG_ddelx * ddelx_dx;
+                    dL_dmy = dL_dG * dG_ddely * ddely_dy;
+                    dL_dcx = -0.5f * gdx * dx * dL_dG;
+                    dL_dcy = -0.5f * gdx * dy * dL_dG;
+                    dL_dcw = -0.5f * gdy * dy * dL_dG;
+                    dL_dop = G * dL_dalpha;
+                }
+            }
+            if (!__any_sync(0xffffffffu, active)) continue;
+            dL_dmx = warp_sum(dL_dmx); dL_dmy = warp_sum(dL_dmy);
+            dL_dcx = warp_sum(dL_dcx); dL_dcy = warp_sum(dL_dcy); dL_dcw = warp_sum(dL_dcw);
+            dL_dop = warp_sum(dL_dop);
+            dL_dr = warp_sum(dL_dr); dL_dg = warp_sum(dL_dg); dL_db = warp_sum(dL_db);
+            if ((threadIdx.x & 31) == 0) {
+                const uint32_t id = __float_as_uint(sC[j].y);
+                atomicAdd(&dL_dmeans2D[3 * id], dL_dmx);
+                atomicAdd(&dL_dmeans2D[3 * id + 1], dL_dmy);
+                float* co = reinterpret_cast<float*>(&dL_dconic_op[id]);
+                atomicAdd(co, dL_dcx); atomicAdd(co + 1, dL_dcy); atomicAdd(co + 2, dL_dcw); atomicAdd(co + 3, dL_dop);
+                atomicAdd(&dL_dcolors[3 * id], dL_dr);
+                atomicAdd(&dL_dcolors[3 * id + 1], dL_dg);
+                atomicAdd(&dL_dcolors[3 * id + 2], dL_db);
+            }
+        }
+    }
+}
+
+int launch_render_backward(const Camera& cam, BinningState b, ImageState im, const float* dL_dpix, float* dL_dmeans2D,
+                           float4* dL_dconic_op, float* dL_dcolors, cudaStream_t stream) {
+    dim3 grid(cam.grid_x, cam.grid_y);
+    render_backward_kernel<<<grid, GPSG_TILE_PIX, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges, im.final_T,
+                                                              im.n_contrib, dL_dpix, dL_dmeans2D, dL_dconic_op,
+                                                              dL_dcolors);
+    GPSG_LAUNCH_CHECK();
+    return GPSG_OK;
+}
+
+// A.7 + A.8 fused: per Gaussian, (dL/dmean2D, dL/dconic) -> dL/d{mean3D, cov3D, scale, rotation}.
+__global__ void __launch_bounds__(256) preprocess_backward_kernel(
+    const __grid_constant__ Camera cam, int P, const float* __restrict__ means3D, const int32_t* __restrict__ radii,
+    const float* __restrict__ scales, const float* __restrict__ rots, const float* __restrict__ cov3D_precomp,
+    const float* __restrict__ dL_dmeans2D, const float4* __restrict__ dL_dconic_op, float* __restrict__ dL_dopacity,
+    float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dscales,
+    float* __restrict__ dL_drots) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float dm[3] = {0.f, 0.f, 0.f}, dsc[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
+    float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float dop = 0.f;
+    if (radii[i] > 0) {
+        const float* view = cam.view;
+        const float* proj = cam.proj;
+        const float x = means3D[3 * i], y = means3D[3 * i + 1], z = means3D[3 * i + 2];
+        const float4 gco = dL_dconic_op[i];
+        dop = gco.w;
+        // --- Sigma3D (recomputed; not stored by the forward) ---
+        float c6[6];
+        float R[3][3];
+        float sv[3] = {0.f, 0.f, 0.f};
+        float qr = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+        if (cov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) c6[k] = cov3D_precomp[6 * i + k];
+        } else {
+            qr = rots[4 * i]; qx = rots[4 * i + 1]; qy = rots[4 * i + 2]; qz = rots[4 * i + 3];
+            R[0][0] = 1.f - 2.f * (qy * qy + qz * qz); R[0][1] = 2.f * (qx * qy - qr * qz); R[0][2] = 2.f * (qx * qz + qr * qy);
+            R[1][0] = 2.f * (qx * qy + qr * qz); R[1][1] = 1.f - 2.f * (qx * qx + qz * qz); R[1][2] = 2.f * (qy * qz - qr * qx);
+            R[2][0] = 2.f * (qx * qz - qr * qy); R[2][1] = 2.f * (qy * qz + qr * qx); R[2][2] = 1.f - 2.f * (qx * qx + qy * qy);
+            sv[0] = cam.scale_modifier * scales[3 * i]; sv[1] = cam.scale_modifier * scales[3 * i + 1];
+            sv[2] = cam.scale_modifier * scales[3 * i + 2];
+            // Sigma(a,b) = sum_i R(a,i) s_i^2 R(b,i)
+            float N[3][3];
+#pragma unroll
+            for (int a_ = 0; a_ < 3; ++a_)
+#pragma unroll
+                for (int i_ = 0; i_ < 3; ++i_) N[a_][i_] = R[a_][i_] * sv[i_];
+            c6[0] = N[0][0] * N[0][0] + N[0][1] * N[0][1] + N[0][2] * N[0][2];
+            c6[1] = N[0][0] * N[1][0] + N[0][1] * N[1][1] + N[0][2] * N[1][2];
+            c6[2] = N[0][0] * N[2][0] + N[0][1] * N[2][1] + N[0][2] * N[2][2];
+            c6[3] = N[1][0] * N[1][0] + N[1][1] * N[1][1] + N[1][2] * N[1][2];
+            c6[4] = N[1][0] * N[2][0] + N[1][1] * N[2][1] + N[1][2] * N[2][2];
+            c6[5] = N[2][0] * N[2][0] + N[2][1] * N[2][1] + N[2][2] * N[2][2];
+        }
+        // --- A.7: cov2D backward ---
+        const float tvx = view[0] * x + view[4] * y + view[8] * z + view[12];
+        const float tvy = view[1] * x + view[5] * y + view[9] * z + view[13];
+        const float tvz = view[2] * x + view[6] * y + view[10] * z + view[14];
+        const float limx = 1.3f * cam.tanfovx, limy = 1.3f * cam.tanfovy;
+        const float txtz = tvx / tvz, tytz = tvy / tvz;
+        const float tx = fminf(limx, fmaxf(-limx, txtz)) * tvz;
+        const float ty = fminf(limy, fmaxf(-limy, tytz)) * tvz;
+        const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+        const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+        const float itz = 1.f / tvz, itz2 = itz * itz, itz3 = itz2 * itz;
+        const float J00 = cam.focal_x * itz, J02 = -(cam.focal_x * tx) * itz2;
+        const float J11 = cam.focal_y * itz, J12 = -(cam.focal_y * ty) * itz2;
+        float A0[3], A1[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            A0[k] = view[k * 4 + 0] * J00 + view[k * 4 + 2] * J02;
+            A1[k] = view[k * 4 + 1] * J11 + view[k * 4 + 2] * J12;
+        }
+        const float S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
+        float SA0[3], SA1[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            SA0[k] = S[k][0] * A0[0] + S[k][1] * A0[1] + S[k][2] * A0[2];
+            SA1[k] = S[k][0] * A1[0] + S[k][1] * A1[1] + S[k][2] * A1[2];
+        }
+        const float a = (A0[0] * SA0[0] + A0[1] * SA0[1] + A0[2] * SA0[2]) + 0.3f;
+        const float b = A0[0] * SA1[0] + A0[1] * SA1[1] + A0[2] * SA1[2];
+        const float c = (A1[0] * SA1[0] + A1[1] * SA1[1] + A1[2] * SA1[2]) + 0.3f;
+        const float denom = a * c - b * b;
+        const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+        float dT0[3] = {0.f, 0.f, 0.f}, dT1[3] = {0.f, 0.f, 0.f};
+        if (denom2inv != 0.f) {
+            const float dL_da = denom2inv * (-c * c * gco.x + 2.f * b * c * gco.y + (denom - a * c) * gco.z);
+            const float dL_dc = denom2inv * (-a * a * gco.z + 2.f * a * b * gco.y + (denom - a * c) * gco.x);
+            const float dL_db = denom2inv * 2.f * (b * c * gco.x - (denom + 2.f * b * b) * gco.y + a * b * gco.z);
+            dcov[0] = A0[0] * A0[0] * dL_da + A0[0] * A1[0] * dL_db + A1[0] * A1[0] * dL_dc;
+            dcov[3] = A0[1] * A0[1] * dL_da + A0[1] * A1[1] * dL_db + A1[1] * A1[1] * dL_dc;
+            dcov[5] = A0[2] * A0[2] * dL_da + A0[2] * A1[2] * dL_db + A1[2] * A1[2] * dL_dc;
+            dcov[1] = 2.f * A0[0] * A0[1] * dL_da + (A0[0] * A1[1] + A0[1] * A1[0]) * dL_db + 2.f * A1[0] * A1[1] * dL_dc;
+            dcov[2] = 2.f * A0[0] * A0[2] * dL_da + (A0[0] * A1[2] + A0[2] * A1[0]) * dL_db + 2.f * A1[0] * A1[2] * dL_dc;
+            dcov[4] = 2.f * A0[2] * A0[1] * dL_da + (A0[1] * A1[2] + A0[2] * A1[1]) * dL_db + 2.f * A1[1] * A1[2] * dL_dc;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                dT0[k] = 2.f * SA0[k] * dL_da + SA1[k] * dL_db;
+                dT1[k] = 2.f * SA1[k] * dL_dc + SA0[k] * dL_db;
+            }
+        }
+        float dJ00 = 0.f, dJ02 = 0.f, dJ11 = 0.f, dJ12 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            dJ00 += view[k * 4 + 0] * dT0[k];
+            dJ02 += view[k * 4 + 2] * dT0[k];
+            dJ11 += view[k * 4 + 1] * dT1[k];
+            dJ12 += view[k * 4 + 2] * dT1[k];
+        }
+        const float dL_dtx = x_grad_mul * -cam.focal_x * itz2 * dJ02;
+        const float dL_dty = y_grad_mul * -cam.focal_y * itz2 * dJ12;
+        const float dL_dtz = -cam.focal_x * itz2 * dJ00 - cam.focal_y * itz2 * dJ11 +
+                             (2.f * cam.focal_x * tx) * itz3 * dJ02 + (2.f * cam.focal_y * ty) * itz3 * dJ12;
+        dm[0] = view[0] * dL_dtx + view[1] * dL_dty + view[2] * dL_dtz;
+        dm[1] = view[4] * dL_dtx + view[5] * dL_dty + view[6] * dL_dtz;
+        dm[2] = view[8] * dL_dtx + view[9] * dL_dty + view[10] * dL_dtz;
+        // --- A.8: pixel-position path ---
+        const float hw = proj[3] * x + proj[7] * y + proj[11] * z + proj[15];
+        const float m_w = 1.0f / (hw + 0.0000001f);
+        const float mul1 = (proj[0] * x + proj[4] * y + proj[8] * z + proj[12]) * m_w * m_w;
+        const float mul2 = (proj[1] * x + proj[5] * y + proj[9] * z + proj[13]) * m_w * m_w;
+        const float gm0 = dL_dmeans2D[3 * i], gm1 = dL_dmeans2D[3 * i + 1];
+        dm[0] += (proj[0] * m_w - proj[3] * mul1) * gm0 + (proj[1] * m_w - proj[3] * mul2) * gm1;
+        dm[1] += (proj[4] * m_w - proj[7] * mul1) * gm0 + (proj[5] * m_w - proj[7] * mul2) * gm1;
+        dm[2] += (proj[8] * m_w - proj[11] * mul1) * gm0 + (proj[9] * m_w - proj[11] * mul2) * gm1;
+        // --- A.8: Sigma3D -> scale, rotation ---
+        if (!cov3D_precomp) {
+            const float dS[3][3] = {{dcov[0], 0.5f * dcov[1], 0.5f * dcov[2]},
+                                    {0.5f * dcov[1], dcov[3], 0.5f * dcov[4]},
+                                    {0.5f * dcov[2], 0.5f * dcov[4], dcov[5]}};
+            float dR[3][3];
+#pragma unroll
+            for (int i_ = 0; i_ < 3; ++i_) {
+                float acc_s = 0.f;
+#pragma unroll
+                for (int a_ = 0; a_ < 3; ++a_) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int b_ = 0; b_ < 3; ++b_) acc += dS[a_][b_] * (R[b_][i_] * sv[i_]);
+                    const float dN = 2.f * acc;
+                    acc_s += dN * R[a_][i_];
+                    dR[a_][i_] = dN * sv[i_];
+                }
+                dsc[i_] = cam.scale_modifier * acc_s;
+            }
+            dq[0] = 2.f * (-qz * dR[0][1] + qy * dR[0][2] + qz * dR[1][0] - qx * dR[1][2] - qy * dR[2][0] + qx * dR[2][1]);
+            dq[1] = 2.f * (qy * dR[0][1] + qz * dR[0][2] + qy * dR[1][0] - 2.f * qx * dR[1][1] - qr * dR[1][2] + qz * dR[2][0] + qr * dR[2][1] - 2.f * qx * dR[2][2]);
+            dq[2] = 2.f * (-2.f * qy * dR[0][0] + qx * dR[0][1] + qr * dR[0][2] + qx * dR[1][0] + qz * dR[1][2] - qr * dR[2][0] + qz * dR[2][1] - 2.f * qy * dR[2][2]);
+            dq[3] = 2.f * (-2.f * qz * dR[0][0] - qr * dR[0][1] + qx * dR[0][2] + qr * dR[1][0] - 2.f * qz * dR[1][1] + qy * dR[1][2] + qx * dR[2][0] + qy * dR[2][1]);
+        }
+    }
+    dL_dopacity[i] = dop;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dL_dmeans3D[3 * i + k] = dm[k];
+    if (dL_dcov3D) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) dL_dcov3D[6 * i + k] = dcov[k];
+    }
+    if (dL_dscales) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dL_dscales[3 * i + k] = dsc[k];
+    }
+    if (dL_drots) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dL_drots[4 * i + k] = dq[k];
+    }
+}
+
+int launch_preprocess_backward(const Camera& cam, int P, const float* means3D, const int32_t* radii,
+                               const float* scales, const float* rots, const float* cov3D_precomp,
+                               const float* dL_dmeans2D, const float4* dL_dconic_op, float* dL_dopacity,
+                               float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales, float* dL_drots,
+                               cudaStream_t stream) {
+    if (P <= 0) return GPSG_OK;
+    preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(cam, P, means3D, radii, scales, rots,
+                                                                   cov3D_precomp, dL_dmeans2D, dL_dconic_op,
+                                                                   dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dscales,
+                                                                   dL_drots);
+    GPSG_LAUNCH_CHECK();
+    return GPSG_OK;
+}
+
+}  // namespace gpsg

@@ -1,0 +1,183 @@
+"""Drop-in `diff_gaussian_rasterization` for GPS-Gaussian, backed by libgpsg_sm100.so (sm_100a).
+
+Put `gps-gaussian_b200/dropin` on PYTHONPATH and the UNMODIFIED reference imports this module at
+gaussian_renderer/__init__.py:14 instead of the third-party extension
+(graphdeco-inria/diff-gaussian-rasterization, pre-`antialiasing` API -- SURVEY.md Appendix A.1).
+
+Same surface: `GaussianRasterizationSettings` (exactly the 12 fields used at
+gaussian_renderer/__init__.py:36-49), `GaussianRasterizer(raster_settings)(means3D, means2D,
+opacities, shs, colors_precomp, scales, rotations, cov3D_precomp) -> (color[3,H,W], radii[P])`,
+`GaussianRasterizer.markVisible`, `rasterize_gaussians`.  Same error behaviour for the
+"exactly one of" argument checks.
+"""
+import ctypes as C
+import os
+import sys
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+_REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+if _REPO not in sys.path:
+    sys.path.insert(0, _REPO)
+from gps_gaussian_b200 import _lib  # noqa: E402  (raises if the CUDA library is not built)
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+def _host_floats(t, n):
+    """n floats of a tensor that may live on CPU (training: pinned host, reference
+    train_stage2.py:155-157) or CUDA (test scripts, reference lib/utils.py:49-53)."""
+    if isinstance(t, torch.Tensor):
+        v = t.detach().to(device="cpu", dtype=torch.float32).reshape(-1).tolist()
+    else:
+        v = [float(x) for x in t]
+    if len(v) != n:
+        raise ValueError(f"expected {n} values, got {len(v)}")
+    return v
+
+
+def _pack_settings(rs):
+    s = _lib.RasterSettings()
+    s.image_height, s.image_width = int(rs.image_height), int(rs.image_width)
+    s.tanfovx, s.tanfovy = float(rs.tanfovx), float(rs.tanfovy)
+    s.bg[:] = _host_floats(rs.bg, 3)
+    s.scale_modifier = float(rs.scale_modifier)
+    s.viewmatrix[:] = _host_floats(rs.viewmatrix, 16)
+    s.projmatrix[:] = _host_floats(rs.projmatrix, 16)
+    s.sh_degree = int(rs.sh_degree)
+    s.campos[:] = _host_floats(rs.campos, 3)
+    s.prefiltered, s.debug = int(bool(rs.prefiltered)), int(bool(rs.debug))
+    return s
+
+
+def _f32c(t):
+    return t.detach().to(dtype=torch.float32).contiguous()
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if (t is not None and t.numel() > 0) else None
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        if not means3D.is_cuda:
+            raise RuntimeError("diff_gaussian_rasterization (gpsg_sm100): means3D must be a CUDA tensor")
+        dev = means3D.device
+        P = int(means3D.shape[0])
+        H, W = int(raster_settings.image_height), int(raster_settings.image_width)
+        settings = _pack_settings(raster_settings)
+        m3 = _f32c(means3D)
+        col = _f32c(colors_precomp) if colors_precomp.numel() else None
+        shs = _f32c(sh) if sh.numel() else None
+        op = _f32c(opacities)
+        sc = _f32c(scales) if scales.numel() else None
+        ro = _f32c(rotations) if rotations.numel() else None
+        cp = _f32c(cov3Ds_precomp) if cov3Ds_precomp.numel() else None
+        sh_M = int(shs.shape[1]) if shs is not None else 0
+        color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        num_rendered = C.c_int32(0)
+        _lib.begin_alloc(dev)
+        try:
+            with torch.cuda.device(dev):
+                rc = _lib.lib.gpsg_rasterize_forward(
+                    C.byref(settings), dev.index if dev.index is not None else torch.cuda.current_device(),
+                    _stream(dev), P, sh_M, _ptr(m3), _ptr(col), _ptr(shs), _ptr(op), _ptr(sc), _ptr(ro), _ptr(cp),
+                    _ptr(color), _ptr(radii), _lib.ALLOC_CB, C.c_void_p(1), _lib.ALLOC_CB, C.c_void_p(2),
+                    _lib.ALLOC_CB, C.c_void_p(3), C.byref(num_rendered))
+        finally:
+            bufs = _lib.end_alloc()
+        _lib.check(rc, "gpsg_rasterize_forward")
+        ctx.settings = settings
+        ctx.num_rendered = int(num_rendered.value)
+        ctx.bufs = (bufs.get(1), bufs.get(2), bufs.get(3))
+        ctx.opt = (col is not None, shs is not None, sc is not None, ro is not None, cp is not None, sh_M)
+        ctx.save_for_backward(*[t if t is not None else torch.empty(0, device=dev) for t in
+                                (m3, col, shs, op, sc, ro, cp, radii)])
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii):
+        m3, col, shs, op, sc, ro, cp, radii = ctx.saved_tensors
+        has_col, has_sh, has_sc, has_ro, has_cp, sh_M = ctx.opt
+        dev = m3.device
+        P = int(m3.shape[0])
+        g = _f32c(grad_out_color)
+        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        d_means2D, d_colors, d_opacity, d_means3D = new(P, 3), new(P, 3), new(P, 1), new(P, 3)
+        d_scales, d_rots = new(P, 3), new(P, 4)
+        d_cov3D = new(P, 6) if has_cp else None
+        ws = torch.empty(int(_lib.lib.gpsg_rasterize_backward_workspace_bytes(P)), dtype=torch.uint8, device=dev)
+        geom, binning, image = ctx.bufs
+        if P > 0:
+            with torch.cuda.device(dev):
+                rc = _lib.lib.gpsg_rasterize_backward(
+                    C.byref(ctx.settings), dev.index if dev.index is not None else torch.cuda.current_device(),
+                    _stream(dev), P, sh_M, ctx.num_rendered, _ptr(m3), _ptr(col) if has_col else None,
+                    _ptr(shs) if has_sh else None, _ptr(op), _ptr(sc) if has_sc else None,
+                    _ptr(ro) if has_ro else None, _ptr(cp) if has_cp else None, _ptr(radii), _ptr(geom),
+                    _ptr(binning), _ptr(image), _ptr(g), _ptr(d_means2D), _ptr(d_colors), _ptr(d_opacity),
+                    _ptr(d_means3D), _ptr(d_cov3D), None, _ptr(d_scales), _ptr(d_rots), _ptr(ws))
+            _lib.check(rc, "gpsg_rasterize_backward")
+        # input order: means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, settings
+        return (d_means3D, d_means2D, None, d_colors if has_col else None, d_opacity,
+                d_scales if has_sc else None, d_rots if has_ro else None, d_cov3D, None)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            p = _f32c(positions)
+            dev = p.device
+            out = torch.empty((p.shape[0],), dtype=torch.uint8, device=dev)
+            view = (C.c_float * 16)(*_host_floats(self.raster_settings.viewmatrix, 16))
+            with torch.cuda.device(dev):
+                rc = _lib.lib.gpsg_mark_visible(dev.index if dev.index is not None else torch.cuda.current_device(),
+                                                _stream(dev), int(p.shape[0]), _ptr(p), view, _ptr(out))
+            _lib.check(rc, "gpsg_mark_visible")
+        return out.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        e = torch.Tensor([])
+        return rasterize_gaussians(means3D, means2D, shs if shs is not None else e,
+                                   colors_precomp if colors_precomp is not None else e, opacities,
+                                   scales if scales is not None else e, rotations if rotations is not None else e,
+                                   cov3D_precomp if cov3D_precomp is not None else e, self.raster_settings)

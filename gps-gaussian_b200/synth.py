@@ -86,8 +86,18 @@ def novel_camera(K0, E0, K1, E1, width, height, ratio=0.5, znear=ZNEAR, zfar=ZFA
                 width=int(width), height=int(height), K=K, E=np.concatenate([R, t[:, None]], 1))
 
 
+_DEPTH_CACHE = {}
+
+
 def _capsule_depth(K, E, res, radius, y0, y1):
     """Ray-cast a y-axis capsule (segment (0,y0,0)-(0,y1,0), given radius). Returns z-depth [res,res], 0 = miss."""
+    key = (K.tobytes(), E.tobytes(), res, radius, y0, y1)
+    if key not in _DEPTH_CACHE:
+        _DEPTH_CACHE[key] = _capsule_depth_impl(K, E, res, radius, y0, y1)
+    return _DEPTH_CACHE[key]
+
+
+def _capsule_depth_impl(K, E, res, radius, y0, y1):
     R, t = E[:, :3], E[:, 3]
     o = -R.T @ t
     v, u = np.meshgrid(np.arange(res) + 0.5, np.arange(res) + 0.5, indexing="ij")
@@ -125,7 +135,7 @@ def _attrs(rng, n, z_over_fx):
     return rot, scale, opacity, rgb
 
 
-def source_view_maps(res, angle_deg, seed, body_radius=0.40):
+def source_view_maps(res, angle_deg, seed, body_radius=0.425):
     """One source view in the layout lib/network.py writes into data[view]: pixel-aligned maps.
     Returns dict(K, E, depth[res,res], valid[res*res] bool, xyz[res*res,3], img[3,res,res] in [-1,1],
     rot_maps[4,res,res], scale_maps[3,res,res], opacity_maps[1,res,res])  (all float32)."""
@@ -165,7 +175,7 @@ def gather_valid(views):
     return {k: np.ascontiguousarray(np.concatenate(v, 0)) for k, v in out.items()}
 
 
-def stereo_pair_scene(src_res=1024, render_res=None, seed=SEED, ratio=0.5, body_radius=0.40, bg=(0.0, 0.0, 0.0),
+def stereo_pair_scene(src_res=1024, render_res=None, seed=SEED, ratio=0.5, body_radius=0.425, bg=(0.0, 0.0, 0.0),
                       keep_maps=False):
     """BASELINE C2/C4 unit: two source views at +-11.25 deg -> ~P pixel-aligned Gaussians + the novel camera.
     Returns the flat rasterizer inputs exactly as gaussian_renderer.render() receives them."""

@@ -1,0 +1,144 @@
+/*
+ * gpsg.h -- C ABI of libgpsg_sm100.so: the B200 (sm_100a) splat rasterizer and 1-D stereo
+ * correlation sampler behind GPS-Gaussian's hot path.
+ *
+ * The reference has no native code of its own; its FFI for this path is the pybind surface of
+ * two third-party extensions it imports by name:
+ *   - `diff_gaussian_rasterization._C`  (reference gaussian_renderer/__init__.py:14; called through
+ *      GaussianRasterizer at :51-62)          -> rasterize_gaussians / rasterize_gaussians_backward /
+ *                                                mark_visible
+ *   - `corr_sampler`                    (reference core/corr.py:5-8; called at :22 and :28)
+ *                                             -> forward / backward
+ * Each entry point below replaces exactly one of those bound functions; plain pointers and sizes,
+ * no torch/ATen types, no exceptions.  All pointers are DEVICE pointers unless marked host.
+ * Every function returns 0 on success or a negative GPSG_E_* code; gpsg_last_error() gives the
+ * message (thread-local).  All work is enqueued on `stream` (a cudaStream_t) of CUDA device `device`.
+ */
+#ifndef GPSG_H
+#define GPSG_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GPSG_API __attribute__((visibility("default")))
+#else
+#define GPSG_API
+#endif
+
+#define GPSG_OK 0
+#define GPSG_E_INVALID (-1)   /* bad argument (shape / null / unsupported combination) */
+#define GPSG_E_CUDA (-2)      /* a CUDA runtime call or kernel launch failed */
+#define GPSG_E_ALLOC (-3)     /* an allocator callback returned NULL */
+#define GPSG_E_CAPACITY (-4)  /* caller-provided workspace too small */
+
+/* Mirrors diff_gaussian_rasterization.GaussianRasterizationSettings -- the 12 fields the reference
+ * fills at gaussian_renderer/__init__.py:36-49.  Matrices are the 16 floats of the tensors the
+ * reference passes (world_view_transform = W2V^T, full_proj_transform), i.e. the maths matrix is
+ * M(r,c) = m[c*4+r].  Passed BY VALUE into kernels, so the tensors may live on host or device
+ * (in training they stay in pinned host memory: reference train_stage2.py:155-157). */
+typedef struct GpsgRasterSettings {
+    int32_t image_height;
+    int32_t image_width;
+    float tanfovx;
+    float tanfovy;
+    float bg[3];
+    float scale_modifier;
+    float viewmatrix[16];
+    float projmatrix[16];
+    int32_t sh_degree;
+    float campos[3];
+    int32_t prefiltered;
+    int32_t debug;
+} GpsgRasterSettings;
+
+/* Scratch allocator, the C form of upstream's `std::function<char*(size_t)>` resize callbacks over
+ * torch byte tensors: must return a device pointer to >= `bytes` bytes (256-B aligned), valid until
+ * the matching backward call has finished.  Called at most once per buffer per forward. */
+typedef void* (*gpsg_alloc_fn)(void* user, size_t bytes);
+
+GPSG_API const char* gpsg_last_error(void);
+GPSG_API int gpsg_version(void);
+
+/* ---- replaces _C.rasterize_gaussians ---------------------------
+ * means3D[P,3] opacities[P] ; exactly one of colors_precomp[P,3] / shs[P,sh_M,3] ; either
+ * (scales[P,3], rotations[P,4]) or cov3D_precomp[P,6].  Outputs out_color[3,H,W], radii[P].
+ * Scratch comes from the three callbacks (geometry / binning / image state, kept for backward).
+ * *num_rendered (HOST) receives the number of (tile,Gaussian) pairs.  One host sync, as upstream. */
+GPSG_API int gpsg_rasterize_forward(const GpsgRasterSettings* settings, int device, void* stream, int P, int sh_M,
+                           const float* means3D, const float* colors_precomp, const float* shs,
+                           const float* opacities, const float* scales, const float* rotations,
+                           const float* cov3D_precomp, float* out_color, int32_t* radii,
+                           gpsg_alloc_fn geom_alloc, void* geom_user, gpsg_alloc_fn binning_alloc,
+                           void* binning_user, gpsg_alloc_fn image_alloc, void* image_user,
+                           int32_t* num_rendered);
+
+/* ---- replaces _C.rasterize_gaussians_backward (Appendix A.6-A.8) ----------------------------
+ * geom/binning/image buffers are the ones the forward allocated.  All dL_* outputs are written
+ * (zero for culled Gaussians); dL_dmeans2D is [P,3] (z unused), dL_dcov3D [P,6] and dL_dsh
+ * [P,sh_M,3] may be NULL when not needed.  `workspace` must hold gpsg_rasterize_backward_workspace_bytes(P). */
+GPSG_API size_t gpsg_rasterize_backward_workspace_bytes(int P);
+GPSG_API int gpsg_rasterize_backward(const GpsgRasterSettings* settings, int device, void* stream, int P, int sh_M,
+                            int32_t num_rendered, const float* means3D, const float* colors_precomp,
+                            const float* shs, const float* opacities, const float* scales, const float* rotations,
+                            const float* cov3D_precomp, const int32_t* radii, const void* geom_buffer,
+                            const void* binning_buffer, const void* image_buffer, const float* dL_dout_color,
+                            float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D,
+                            float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drotations,
+                            void* workspace);
+
+/* ---- replaces _C.mark_visible : present[P] (uint8) = view-space z > 0.2 ---------------------- */
+GPSG_API int gpsg_mark_visible(int device, void* stream, int P, const float* means3D, const float* viewmatrix_host16,
+                      uint8_t* present);
+
+/* Introspection of the saved buffers (used by the parity tests: "tile indices bit-exact").
+ * Each returns a device pointer INTO the given buffer. */
+typedef struct GpsgGeomView {
+    const float* depths;         /* [P] */
+    const float* means2D;        /* [P,2] */
+    const float* conic_opacity;  /* [P,4] */
+    const uint32_t* tiles_touched; /* [P] */
+    const uint32_t* point_offsets; /* [P] inclusive scan */
+} GpsgGeomView;
+typedef struct GpsgBinningView {
+    const uint64_t* point_list_keys; /* [N] sorted */
+    const uint32_t* point_list;      /* [N] sorted Gaussian ids */
+} GpsgBinningView;
+typedef struct GpsgImageView {
+    const float* final_T;       /* [H*W] */
+    const uint32_t* n_contrib;  /* [H*W] */
+    const uint32_t* ranges;     /* [tiles,2] */
+} GpsgImageView;
+GPSG_API int gpsg_geom_view(const void* geom_buffer, int P, GpsgGeomView* out);
+GPSG_API int gpsg_binning_view(const void* binning_buffer, int64_t num_rendered, GpsgBinningView* out);
+GPSG_API int gpsg_image_view(const void* image_buffer, int W, int H, GpsgImageView* out);
+
+/* ---- replaces corr_sampler.forward (reference core/corr.py:22) ---------
+ * volume[B,H,W1,W2] with element strides (sb,sh,sw1; innermost contiguous), dtype 0=fp32 1=fp16;
+ * coords: fp32, element (n,y,x) at coords[n*coords_sb + y*W1 + x] (channel 0 of [B,C,H,W1]);
+ * out[B,2r+1,H,W1] contiguous, dtype of volume. */
+GPSG_API int gpsg_corr_sampler_forward(int device, void* stream, int dtype, int B, int H, int W1, int W2, const void* volume,
+                              int64_t sb, int64_t sh, int64_t sw1, const float* coords, int64_t coords_sb,
+                              int radius, void* out);
+/* ---- replaces corr_sampler.backward (reference core/corr.py:28) -------------------------------
+ * grad_out[B,2r+1,H,W1] contiguous -> grad_volume[B,H,W1,W2] contiguous (fully written). */
+GPSG_API int gpsg_corr_sampler_backward(int device, void* stream, int dtype, int B, int H, int W1, int W2,
+                               const float* coords, int64_t coords_sb, const void* grad_out, int radius,
+                               void* grad_volume);
+
+/* ---- measurement hooks (used by bench.py; off by default) -----------------------------------
+ * When enabled, every stage of the forward/backward is bracketed by CUDA events on the launching stream.
+ * gpsg_profile_read() synchronises, then returns for stage i: total_ms[i] (summed over the calls since the last
+ * reset), calls[i] and the number of kernel launches[i]; it returns the number of stages (names via
+ * gpsg_profile_stage_name) and resets the accumulators.  Thread-local. */
+GPSG_API int gpsg_profile_enable(int on);
+GPSG_API int gpsg_profile_read(float* total_ms, int32_t* calls, int32_t* launches, int capacity);
+GPSG_API const char* gpsg_profile_stage_name(int stage);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPSG_H */

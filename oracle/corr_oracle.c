@@ -16,7 +16,8 @@
 
 /* volume[b,h,w1,w2] = sum_d f1[b,d,h,w1] f2[b,d,h,w2] / sqrt(D)   (core/corr.py:54-61) */
 void SUFFIX(oracle_corr_volume)(int B, int D, int H, int W1, int W2, const real* f1, const real* f2, real* vol) {
-    const real inv = RC(1.0) / R_SQRT((real)D);
+    /* the reference divides by torch.sqrt(torch.tensor(D).float()): an fp32 square root, then a division */
+    const real scale = (real)sqrtf((float)D);
     for (int b = 0; b < B; ++b)
         for (int h = 0; h < H; ++h)
             for (int x = 0; x < W1; ++x)
@@ -24,7 +25,7 @@ void SUFFIX(oracle_corr_volume)(int B, int D, int H, int W1, int W2, const real*
                     real acc = 0;
                     for (int d = 0; d < D; ++d)
                         acc += f1[(((size_t)b * D + d) * H + h) * W1 + x] * f2[(((size_t)b * D + d) * H + h) * W2 + y];
-                    vol[(((size_t)b * H + h) * W1 + x) * W2 + y] = acc * inv;
+                    vol[(((size_t)b * H + h) * W1 + x) * W2 + y] = acc / scale;
                 }
 }
 

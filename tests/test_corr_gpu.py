@@ -1,0 +1,99 @@
+"""GPU parity of the sm_100a correlation sampler: golden vectors from the reference's CorrBlock1D,
+the CPU oracle at larger sizes, fp16 volumes (stage-2 AMP), edge cases.  Through the drop-in
+`corr_sampler` module (== C-ABI via ctypes)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gps_gaussian_b200 import synth
+from oracle.corr_oracle import CorrOracle
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "corr_golden.npz"))
+
+
+def _cuda(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dtype)
+
+
+def test_sampler_forward_backward_golden():
+    import corr_sampler
+    coords = _cuda(G["coords"])
+    for i in range(4):
+        vol = _cuda(G[f"level{i}"])
+        out, = corr_sampler.forward(vol, coords[:, [0]] / 2 ** i, 4)
+        assert out.shape == (2, 9, 3, 40) and out.dtype == torch.float32
+        assert np.abs(out.cpu().numpy() - G["out"][:, 9 * i:9 * i + 9]).max() < 2e-5     # fp32 coords/2^i and weights
+        gv, = corr_sampler.backward(vol, coords[:, [0]] / 2 ** i, _cuda(G["grad_out"][:, 9 * i:9 * i + 9]), 4)
+        assert gv.shape == vol.shape
+        assert np.abs(gv.cpu().numpy() - G[f"grad_level{i}"]).max() < 2e-5
+
+
+def test_corr_block_fast_matches_reference_block_golden():
+    """Mirrored CorrBlockFast1D(fmap1, fmap2)(coords) == reference CorrBlock1D output (golden), incl. autograd."""
+    from gps_gaussian_b200.corr import CorrBlockFast1D
+    f1 = _cuda(G["fmap1"]).requires_grad_(True)
+    f2 = _cuda(G["fmap2"]).requires_grad_(True)
+    blk = CorrBlockFast1D(f1, f2, num_levels=4, radius=4)
+    out = blk(_cuda(G["coords"]))
+    assert out.shape == (2, 36, 3, 40)
+    assert np.abs(out.detach().cpu().numpy() - G["out"]).max() < 5e-5
+    (out * _cuda(G["grad_out"])).sum().backward()
+    assert f1.grad is not None and torch.isfinite(f1.grad).all() and float(f1.grad.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.float16, 4e-3)])
+def test_sampler_vs_oracle_large(dtype, tol):
+    """BASELINE-size feature maps: [2,192,128,128] -> volume [2,128,128,128] (level 0) and a pooled level."""
+    import corr_sampler
+    f1, f2, coords = synth.corr_inputs(2, 16, 128, 128)
+    o = CorrOracle("f32")
+    pyr = o.pyramid(f1, f2, 3)
+    for i in (0, 2):
+        volq = _cuda(pyr[i], dtype)
+        ref_in = volq.float().cpu().numpy()                       # oracle sees the same (quantised) values
+        cx = (coords[:, 0] / np.float32(2 ** i)).astype(np.float32)
+        out, = corr_sampler.forward(volq, _cuda(coords) / 2 ** i, 4)
+        assert out.dtype == dtype
+        want = o.sample_fwd(ref_in, cx, 4)
+        assert np.abs(out.float().cpu().numpy() - want).max() < tol * max(1.0, np.abs(want).max())
+        go = np.random.default_rng(i).standard_normal(want.shape).astype(np.float32)
+        goq = _cuda(go, dtype)
+        gv, = corr_sampler.backward(volq, _cuda(coords) / 2 ** i, goq, 4)
+        wantg = o.sample_bwd(ref_in.shape, cx, goq.float().cpu().numpy(), 4)
+        assert np.abs(gv.float().cpu().numpy() - wantg).max() < tol * max(1.0, np.abs(wantg).max())
+
+
+def test_sampler_edge_cases():
+    import corr_sampler
+    o = CorrOracle("f32")
+    rng = np.random.default_rng(0)
+    # odd sizes, radius != 4, everything out of range, integer coords, non-contiguous coords channel
+    vol = rng.standard_normal((1, 3, 5, 7)).astype(np.float32)
+    coords = np.stack([rng.uniform(-20, 30, (1, 3, 5)), np.zeros((1, 3, 5))], 1).astype(np.float32)
+    coords[0, 0, 0, :3] = [-100.0, 3.0, 1e6]
+    for r in (1, 4, 6):
+        out, = corr_sampler.forward(_cuda(vol), _cuda(coords), r)
+        assert np.abs(out.cpu().numpy() - o.sample_fwd(vol, coords[:, 0], r)).max() < 1e-5
+        go = rng.standard_normal(out.shape).astype(np.float32)
+        gv, = corr_sampler.backward(_cuda(vol), _cuda(coords), _cuda(go), r)
+        assert np.abs(gv.cpu().numpy() - o.sample_bwd(vol.shape, coords[:, 0], go, r)).max() < 1e-5
+    # empty batch
+    out, = corr_sampler.forward(torch.zeros(0, 3, 5, 7, device="cuda"), torch.zeros(0, 1, 3, 5, device="cuda"), 4)
+    assert out.shape == (0, 9, 3, 5)
+
+
+def test_autograd_sampler_linear_and_adjoint():
+    """<S(v), g> == <v, S^T(g)>: forward and backward are exact adjoints (size-independent property)."""
+    from gps_gaussian_b200.corr import CorrSampler
+    gen = torch.Generator("cuda").manual_seed(0)
+    vol = torch.randn(2, 32, 64, 48, device="cuda", generator=gen, requires_grad=True)
+    coords = torch.rand(2, 1, 32, 64, device="cuda", generator=gen) * 60 - 6
+    out = CorrSampler.apply(vol, coords, 4)
+    g = torch.randn(out.shape, device="cuda", generator=gen)
+    (out * g).sum().backward()
+    lhs = float((out.detach().double() * g.double()).sum())
+    rhs = float((vol.detach().double() * vol.grad.double()).sum())
+    assert abs(lhs - rhs) < 1e-3 * max(1.0, abs(lhs))
