@@ -63,9 +63,9 @@ struct BinningState {
     uint32_t* vals_unsorted;  // [N]
     uint64_t* keys;           // [N] sorted (tile<<32 | depth bits)
     uint32_t* vals;           // [N] sorted Gaussian ids ("point_list")
-    float4* slabA;            // [N] (x, y, conic.x, conic.y)          sorted, tile-contiguous
-    float4* slabB;            // [N] (conic.z, opacity, r, g)
-    float4* slabC;            // [N] (b, id bits, 0, 0)
+    float4* slabA;            // [N] (x, y, cull half-extent x, y)     sorted, tile-contiguous
+    float4* slabB;            // [N] (conic.x, conic.y, conic.z, opacity)
+    float4* slabC;            // [N] (r, g, b, Gaussian id bits)
     void* sort_temp;
     size_t sort_temp_bytes;
     static size_t required(size_t N, size_t sort_temp_bytes);

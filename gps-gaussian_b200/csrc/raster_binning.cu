@@ -92,9 +92,22 @@ __global__ void __launch_bounds__(256) gather_ranges_kernel(size_t N, const floa
     const float2 xy = g.means2D[id];
     const float4 co = g.conic_opacity[id];
     const float r = colors[3 * id], gg = colors[3 * id + 1], bb = colors[3 * id + 2];
-    b.slabA[i] = make_float4(xy.x, xy.y, co.x, co.y);
-    b.slabB[i] = make_float4(co.z, co.w, r, gg);
-    b.slabC[i] = make_float4(bb, __uint_as_float(id), 0.0f, 0.0f);
+    // Conservative screen-space half-extents of the region where alpha = o*exp(power) can reach 1/255:
+    // power >= -tau, tau = ln(255 o)  <=>  d^T Conic d <= 2 tau  -> bounding box sqrt(2 tau * Sigma_xx/yy),
+    // Sigma = Conic^-1.  Used only to SKIP work that the per-pixel tests would reject anyway (results unchanged).
+    float ex = 3.0e38f, ey = 3.0e38f;                       // degenerate conic: never cull
+    const float detc = co.x * co.z - co.y * co.y;
+    if (!(co.w * 255.0f >= 1.0f)) {
+        ex = ey = -3.0e38f;                                  // alpha < 1/255 everywhere: always culled
+    } else if (detc > 0.0f && co.x > 0.0f && co.z > 0.0f) {
+        const float tau2 = 2.0f * __logf(co.w * 255.0f) * 1.0005f + 1e-4f;
+        ex = sqrtf(tau2 * co.z / detc) * 1.0005f + 0.01f;
+        ey = sqrtf(tau2 * co.x / detc) * 1.0005f + 0.01f;
+        if (!(ex == ex) || !(ey == ey)) { ex = 3.0e38f; ey = 3.0e38f; }
+    }
+    b.slabA[i] = make_float4(xy.x, xy.y, ex, ey);
+    b.slabB[i] = make_float4(co.x, co.y, co.z, co.w);
+    b.slabC[i] = make_float4(r, gg, bb, __uint_as_float(id));
 }
 
 int launch_gather_ranges(const Camera& cam, size_t N, const float* colors, GeomState g, BinningState b, ImageState im,
