@@ -16,7 +16,6 @@ oracle PORT of the same algorithm on the host cores (the one other place bench.p
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -42,49 +41,59 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (NVML; same fields as the nvidia-smi recipe
+    in B200_PROFILING.md: clocks.sm, clocks.max.sm, clocks_event_reasons.*)."""
 
-    def __init__(self, gpu_index):
-        self.idx = gpu_index
-        self.rows = []
-        self.proc = None
+    def __init__(self, gpu_index, period_s=0.01):
+        self.idx, self.period = gpu_index, period_s
+        self.sm, self.reasons, self.power = [], set(), []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.max_mhz = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {"hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = int(get_reasons(h))
+                        for n, bit in names.items():
+                            if r & bit:
+                                self.reasons.add(n)
+                        self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    except Exception as e:  # keep sampling
+                        self.err = repr(e)
+                    time.sleep(self.period)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception as e:
+            self.err = repr(e)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=2)
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.sm),
+               "power_w_max": max(self.power) if self.power else None}
+        if self.err and not self.sm:
+            out["error"] = self.err
+        return out
 
 
 def _scenes(n, first_seed):
@@ -152,7 +161,7 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--views", type=int, default=8, help="view-pairs per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

@@ -64,7 +64,7 @@ struct BinningState {
     uint64_t* keys;           // [N] sorted (tile<<32 | depth bits)
     uint32_t* vals;           // [N] sorted Gaussian ids ("point_list")
     float4* slabA;            // [N] (x, y, cull half-extent x, y)     sorted, tile-contiguous
-    float4* slabB;            // [N] (conic.x, conic.y, conic.z, opacity)
+    float4* slabB;            // [N] (-0.5*log2e*conic.x, -log2e*conic.y, -0.5*log2e*conic.z, opacity)
     float4* slabC;            // [N] (r, g, b, Gaussian id bits)
     void* sort_temp;
     size_t sort_temp_bytes;

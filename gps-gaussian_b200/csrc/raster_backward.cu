@@ -2,25 +2,13 @@
 // backward.cu::renderCUDA / computeCov2DCUDA / preprocessCUDA, reached from
 // _RasterizeGaussians.backward behind reference gaussian_renderer/__init__.py:54-62).
 #include "gpsg_internal.cuh"
-#include "tma_bulk.cuh"
+#include "slab_ring.cuh"
 
 namespace gpsg {
 
-bool use_v1_kernels();  // raster_render.cu (GPSG_RENDER_IMPL=v1, A/B timing only)
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-constexpr int kBatch = GPSG_TILE_PIX;
-constexpr int kStages = 2;
-struct __align__(128) RenderStage {
-    float4 A[kBatch];  // x, y, cull half-extent x, y
-    float4 B[kBatch];  // conic.x, conic.y, conic.z, opacity
-    float4 C[kBatch];  // r, g, b, id
-};
+constexpr int kBwdChunk = 128;  // Gaussians per ring stage
+constexpr int kBwdStages = 4;
+constexpr int kBwdWarps = 4;    // consumer warps per CTA: 16 x 8 pixels (half a tile)
 
 // One butterfly exchange step of a reduce-scatter: halves the number of live values per lane.
 // Lanes whose `bit` is set keep the upper half, the others the lower half; out[i] = kept[i] + partner's copy.
@@ -35,286 +23,186 @@ __device__ __forceinline__ void rs_step(float* x, int lane, int bit) {
     }
 }
 
-// A.6: per tile, pixels replay their list back to front.
-//  * slabs staged by TMA bulk copies (double-buffered), starting at the deepest contributor of the tile;
-//  * the same warp-level bounding-box culling as the forward;
-//  * per-pixel gradient terms of TWO surviving Gaussians (18 values) are reduced across the warp with a
-//    butterfly reduce-scatter (21 shuffles instead of 90), leaving one total per lane, then one global RED per
-//    value.  (fp32 shared-memory atomics are CAS loops on sm_100a; global REDs are native.)
-__global__ void __launch_bounds__(256) render_backward_kernel(const __grid_constant__ Camera cam,
-                                                              const float4* __restrict__ slabA,
-                                                              const float4* __restrict__ slabB,
-                                                              const float4* __restrict__ slabC,
-                                                              const uint2* __restrict__ ranges,
-                                                              const float* __restrict__ final_T,
-                                                              const uint32_t* __restrict__ n_contrib,
-                                                              const float* __restrict__ dL_dpix,
-                                                              float* __restrict__ dL_dmeans2D,
-                                                              float4* __restrict__ dL_dconic_op,
-                                                              float* __restrict__ dL_dcolors) {
-    __shared__ RenderStage st[kStages];
-    __shared__ __align__(8) uint64_t full_bar[kStages];
-    __shared__ int s_hi;
+// A.6: per (half) tile, pixels replay their list back to front.
+//  * slabs streamed by the producer lane's TMA bulk copies into the shared-memory ring (slab_ring.cuh), starting
+//    at the deepest contributor of the CTA; consumer warps never block on each other;
+//  * the same warp-level bounding-box culling as the forward, plus skipping everything behind the warp's deepest
+//    contributor;
+//  * per-pixel gradient terms of TWO surviving Gaussians (18 values) are reduced across the warp with a butterfly
+//    reduce-scatter (21 shuffles instead of 90), leaving one total per lane, then one global RED per value
+//    (fp32 shared-memory atomics are CAS loops on sm_100a; global REDs are native).
+__global__ void __launch_bounds__((kBwdWarps + 1) * 32) render_backward_kernel(const __grid_constant__ Camera cam,
+                                                                             const float4* __restrict__ slabA,
+                                                                             const float4* __restrict__ slabB,
+                                                                             const float4* __restrict__ slabC,
+                                                                             const uint2* __restrict__ ranges,
+                                                                             const float* __restrict__ final_T,
+                                                                             const uint32_t* __restrict__ n_contrib,
+                                                                             const float* __restrict__ dL_dpix,
+                                                                             float* __restrict__ dL_dmeans2D,
+                                                                             float4* __restrict__ dL_dconic_op,
+                                                                             float* __restrict__ dL_dcolors) {
+    __shared__ SlabRing<kBwdChunk, kBwdStages> ring;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.y * cam.grid_x + blockIdx.x;
-    const int bx0 = blockIdx.x * GPSG_TILE_X + ((warp & 1) << 3), by0 = blockIdx.y * GPSG_TILE_Y + ((warp >> 1) << 2);
+    const int tile_y = blockIdx.y >> 1, half = blockIdx.y & 1;
+    const int tile = tile_y * cam.grid_x + blockIdx.x;
+    const uint2 range = ranges[tile];
+    const int total = (int)(range.y - range.x);
+
+    // per-pixel state (consumer warps only; the producer warp's lanes map outside and stay inert)
+    const int bx0 = blockIdx.x * GPSG_TILE_X + ((warp & 1) << 3);
+    const int by0 = tile_y * GPSG_TILE_Y + (half << 3) + ((warp >> 1) << 2);
     const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
-    const bool inside = px < cam.W && py < cam.H;
+    const bool inside = warp < kBwdWarps && px < cam.W && py < cam.H;
     const float pixfx = (float)px, pixfy = (float)py;
     const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
-    const uint2 range = ranges[tile];
-    const int total = (int)(range.y - range.x);
     const size_t HW = (size_t)cam.W * cam.H;
     const size_t pid = (size_t)py * cam.W + px;
-
     const float T_final = inside ? final_T[pid] : 0.0f;
     const int last_contributor = inside ? (int)n_contrib[pid] : 0;
+    const int wmax = __reduce_max_sync(0xffffffffu, last_contributor);  // positions >= wmax: nothing to do for this warp
+
+    if (tid == 0) ring_init(ring, kBwdWarps);
+    __syncthreads();
+    if (lane == 0 && wmax > 0) atomicMax(&ring.hi, wmax);
+    __syncthreads();
+    const int hi = min(total, *(volatile int*)&ring.hi);  // only list positions [0, hi) matter for this CTA
+    const int nbatch = (hi + kBwdChunk - 1) / kBwdChunk;
+    // batch b = positions [end - n, end), end = hi - b*chunk  (back to front)
+
+    if (warp == kBwdWarps) {  // ---------------- producer warp ----------------
+        if (lane == 0)
+            ring_produce(ring, nbatch, kBwdWarps, slabA, slabB, slabC,
+                         [&](int b) { const int end = hi - b * kBwdChunk; return (size_t)range.x + (size_t)(end - min(kBwdChunk, end)); },
+                         [&](int b) { return min(kBwdChunk, hi - b * kBwdChunk); });
+        return;
+    }
+
     float T = T_final;
     float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f, lastc0 = 0.f, lastc1 = 0.f, lastc2 = 0.f, last_alpha = 0.f;
     float g0 = 0.f, g1 = 0.f, g2 = 0.f;
     if (inside) { g0 = dL_dpix[pid]; g1 = dL_dpix[HW + pid]; g2 = dL_dpix[2 * HW + pid]; }
     const float bg_dot = (cam.bg[0] * g0 + cam.bg[1] * g1) + cam.bg[2] * g2;
     const float ddelx_dx = 0.5f * (float)cam.W, ddely_dy = 0.5f * (float)cam.H;
-
-    const int wmax = __reduce_max_sync(0xffffffffu, last_contributor);  // list positions >= wmax: nothing to do for this warp
-    if (tid == 0) {
-        s_hi = 0;
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    if (lane == 0 && wmax > 0) atomicMax(&s_hi, wmax);
-    __syncthreads();
-    const int hi = min(total, s_hi);  // only list positions [0, hi) matter for this tile
-    const int nbatch = (hi + kBatch - 1) / kBatch;
-
-    auto issue = [&](int b) {  // thread 0 only; batch b = positions [end - n, end), end = hi - b*kBatch
-        const int s = b % kStages;
-        const int end = hi - b * kBatch;
-        const int n = min(kBatch, end);
-        const uint32_t bytes = (uint32_t)n * 16u;
-        const size_t k = (size_t)range.x + (size_t)(end - n);
-        mbar_expect_tx(&full_bar[s], 3u * bytes);
-        tma_bulk_g2s(st[s].A, slabA + k, bytes, &full_bar[s]);
-        tma_bulk_g2s(st[s].B, slabB + k, bytes, &full_bar[s]);
-        tma_bulk_g2s(st[s].C, slabC + k, bytes, &full_bar[s]);
-    };
-    if (tid == 0) {
-        if (nbatch > 0) issue(0);
-        if (nbatch > 1) issue(1);
-    }
 
     for (int b = 0; b < nbatch; ++b) {
-        const int s = b % kStages;
-        mbar_wait(&full_bar[s], (uint32_t)((b / kStages) & 1));
-        const int end = hi - b * kBatch;
-        const int n = min(kBatch, end);
+        ring_wait_full(ring, b, kBwdWarps + 1 /* never "all done" in the backward */);
+        const int s = b % kBwdStages;
+        const int end = hi - b * kBwdChunk;
+        const int n = min(kBwdChunk, end);
         const int start = end - n;
-        const RenderStage& S = st[s];
-        // two pending Gaussians: x[0..7]/x[8..15] = comps (dmx,dmy,dcx,dcy,dcw,dop,dr,dg), y[0..1] = db
-        float x[16], y[2];
-        int j0 = 0, j1 = 0, slot = 0;
-        auto flush = [&]() {
-            rs_step<16>(x, lane, 16);
-            rs_step<8>(x, lane, 8);
-            rs_step<4>(x, lane, 4);
-            rs_step<2>(x, lane, 2);
-            const float tot = x[0] + __shfl_xor_sync(0xffffffffu, x[0], 1);  // lane l holds total of value l>>1
-            rs_step<2>(y, lane, 16);
-            float tb = y[0];
-            tb += __shfl_xor_sync(0xffffffffu, tb, 8);
-            tb += __shfl_xor_sync(0xffffffffu, tb, 4);
-            tb += __shfl_xor_sync(0xffffffffu, tb, 2);
-            tb += __shfl_xor_sync(0xffffffffu, tb, 1);                       // lanes 0-15: Gaussian 0, 16-31: Gaussian 1
-            const int gsel = lane >> 4;
-            if (gsel < slot) {
-                const uint32_t id = __float_as_uint(S.C[gsel ? j1 : j0].w);
-                if ((lane & 1) == 0) {
-                    const int k = (lane >> 1) & 7;
-                    float* dst = (k < 2) ? (dL_dmeans2D + 3 * (size_t)id + k)
-                                         : (k < 6) ? (reinterpret_cast<float*>(dL_dconic_op + id) + (k - 2))
-                                                   : (dL_dcolors + 3 * (size_t)id + (k - 6));
-                    atomicAdd(dst, tot);
+        if (start < wmax) {
+            const float4* __restrict__ SA = ring.A[s];
+            const float4* __restrict__ SB = ring.B[s];
+            const float4* __restrict__ SC = ring.C[s];
+            // two pending Gaussians: x[0..7]/x[8..15] = comps (dmx,dmy,dcx,dcy,dcw,dop,dr,dg), y[0..1] = db
+            float x[16], y[2];
+            int j0 = 0, j1 = 0, slot = 0;
+            auto flush = [&]() {
+                rs_step<16>(x, lane, 16);
+                rs_step<8>(x, lane, 8);
+                rs_step<4>(x, lane, 4);
+                rs_step<2>(x, lane, 2);
+                const float tot = x[0] + __shfl_xor_sync(0xffffffffu, x[0], 1);  // lane l holds total of value l>>1
+                rs_step<2>(y, lane, 16);
+                float tb = y[0];
+                tb += __shfl_xor_sync(0xffffffffu, tb, 8);
+                tb += __shfl_xor_sync(0xffffffffu, tb, 4);
+                tb += __shfl_xor_sync(0xffffffffu, tb, 2);
+                tb += __shfl_xor_sync(0xffffffffu, tb, 1);                       // lanes 0-15: Gaussian 0, 16-31: Gaussian 1
+                const int gsel = lane >> 4;
+                if (gsel < slot) {
+                    const uint32_t id = __float_as_uint(SC[gsel ? j1 : j0].w);
+                    if ((lane & 1) == 0) {
+                        const int k = (lane >> 1) & 7;
+                        float* dst = (k < 2) ? (dL_dmeans2D + 3 * (size_t)id + k)
+                                             : (k < 6) ? (reinterpret_cast<float*>(dL_dconic_op + id) + (k - 2))
+                                                       : (dL_dcolors + 3 * (size_t)id + (k - 6));
+                        atomicAdd(dst, tot);
+                    }
+                    if ((lane & 15) == 1) atomicAdd(dL_dcolors + 3 * (size_t)id + 2, tb);
                 }
-                if ((lane & 15) == 1) atomicAdd(dL_dcolors + 3 * (size_t)id + 2, tb);
-            }
-            slot = 0;
-        };
-        for (int base = ((n - 1) >> 5) << 5; base >= 0; base -= 32) {
-            if (start + base >= wmax) continue;
-            const int my = base + lane;
-            bool hit = false;
-            if (my < n && start + my < wmax) {
-                const float4 a = S.A[my];
-                hit = (a.x >= wx0 - a.z) && (a.x <= wx1 + a.z) && (a.y >= wy0 - a.w) && (a.y <= wy1 + a.w);
-            }
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-                const int bit = 31 - __clz(m);
-                m &= ~(1u << bit);
-                const int j = base + bit;
-                bool active = (start + j) < last_contributor;   // implies inside
-                float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f, t5 = 0.f, t6 = 0.f, t7 = 0.f, t8 = 0.f;
-                if (active) {
-                    const float4 a = S.A[j];
-                    const float4 q = S.B[j];
-                    const float dx = a.x - pixfx, dy = a.y - pixfy;
-                    const float power = -0.5f * (q.x * dx * dx + q.z * dy * dy) - q.y * dx * dy;
-                    const float G = __expf(power);
-                    const float alpha = fminf(0.99f, q.w * G);
-                    active = !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                slot = 0;
+            };
+            for (int base = ((n - 1) >> 5) << 5; base >= 0; base -= 32) {
+                if (start + base >= wmax) continue;
+                const int my = base + lane;
+                bool hit = false;
+                if (my < n && start + my < wmax) {
+                    const float4 a = SA[my];
+                    hit = (a.x >= wx0 - a.z) && (a.x <= wx1 + a.z) && (a.y >= wy0 - a.w) && (a.y <= wy1 + a.w);
+                }
+                unsigned m = __ballot_sync(0xffffffffu, hit);
+                while (m) {
+                    const int bit = 31 - __clz(m);
+                    m &= ~(1u << bit);
+                    const int j = base + bit;
+                    bool active = (start + j) < last_contributor;   // implies inside
+                    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f, t5 = 0.f, t6 = 0.f, t7 = 0.f, t8 = 0.f;
                     if (active) {
-                        const float4 c = S.C[j];
-                        T = T / (1.0f - alpha);
-                        const float dchannel_dcolor = alpha * T;
-                        accum0 = last_alpha * lastc0 + (1.f - last_alpha) * accum0; lastc0 = c.x;
-                        accum1 = last_alpha * lastc1 + (1.f - last_alpha) * accum1; lastc1 = c.y;
-                        accum2 = last_alpha * lastc2 + (1.f - last_alpha) * accum2; lastc2 = c.z;
-                        float dL_dalpha = (c.x - accum0) * g0;
-                        dL_dalpha += (c.y - accum1) * g1;
-                        dL_dalpha += (c.z - accum2) * g2;
-                        t6 = dchannel_dcolor * g0; t7 = dchannel_dcolor * g1; t8 = dchannel_dcolor * g2;
-                        dL_dalpha *= T;
-                        last_alpha = alpha;
-                        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-                        const float dL_dG = q.w * dL_dalpha;
-                        const float gdx = G * dx, gdy = G * dy;
-                        const float dG_ddelx = -gdx * q.x - gdy * q.y;
-                        const float dG_ddely = -gdy * q.z - gdx * q.y;
-                        t0 = dL_dG * dG_ddelx * ddelx_dx;
-                        t1 = dL_dG * dG_ddely * ddely_dy;
-                        t2 = -0.5f * gdx * dx * dL_dG;
-                        t3 = -0.5f * gdx * dy * dL_dG;
-                        t4 = -0.5f * gdy * dy * dL_dG;
-                        t5 = G * dL_dalpha;
+                        const float2 xy = *reinterpret_cast<const float2*>(&SA[j]);
+                        const float4 q = SB[j];
+                        const float dx = xy.x - pixfx, dy = xy.y - pixfy;
+                        const float p = fmaf(q.z * dy, dy, fmaf(q.x, dx, q.y * dy) * dx);   // log2e * power
+                        const float G = ex2_approx(p);
+                        const float alpha = fminf(0.99f, q.w * G);
+                        active = !(p > 0.0f) && !(alpha < 1.0f / 255.0f);
+                        if (active) {
+                            const float4 c = SC[j];
+                            const float inv1ma = __frcp_rn(1.0f - alpha);
+                            T = T * inv1ma;
+                            const float dchannel_dcolor = alpha * T;
+                            accum0 = last_alpha * lastc0 + (1.f - last_alpha) * accum0; lastc0 = c.x;
+                            accum1 = last_alpha * lastc1 + (1.f - last_alpha) * accum1; lastc1 = c.y;
+                            accum2 = last_alpha * lastc2 + (1.f - last_alpha) * accum2; lastc2 = c.z;
+                            float dL_dalpha = (c.x - accum0) * g0;
+                            dL_dalpha += (c.y - accum1) * g1;
+                            dL_dalpha += (c.z - accum2) * g2;
+                            t6 = dchannel_dcolor * g0; t7 = dchannel_dcolor * g1; t8 = dchannel_dcolor * g2;
+                            dL_dalpha *= T;
+                            last_alpha = alpha;
+                            dL_dalpha = fmaf(-T_final * inv1ma, bg_dot, dL_dalpha);
+                            const float dL_dG = q.w * dL_dalpha;
+                            // conic = (-2 ln2 Bx, -ln2 By, -2 ln2 Bz): dG/ddelx = -G (cx dx + cy dy) = ln2 G (2 Bx dx + By dy)
+                            const float gl = kLn2 * G * dL_dG;
+                            t0 = gl * fmaf(2.0f * q.x, dx, q.y * dy) * ddelx_dx;
+                            t1 = gl * fmaf(2.0f * q.z, dy, q.y * dx) * ddely_dy;
+                            const float h = -0.5f * G * dL_dG;
+                            t2 = h * dx * dx;
+                            t3 = h * dx * dy;
+                            t4 = h * dy * dy;
+                            t5 = G * dL_dalpha;
+                        }
+                    }
+                    if (!__any_sync(0xffffffffu, active)) continue;
+                    if (slot == 0) {
+                        x[0] = t0; x[1] = t1; x[2] = t2; x[3] = t3; x[4] = t4; x[5] = t5; x[6] = t6; x[7] = t7; y[0] = t8;
+                        j0 = j; slot = 1;
+                    } else {
+                        x[8] = t0; x[9] = t1; x[10] = t2; x[11] = t3; x[12] = t4; x[13] = t5; x[14] = t6; x[15] = t7; y[1] = t8;
+                        j1 = j; slot = 2;
+                        flush();
                     }
                 }
-                if (!__any_sync(0xffffffffu, active)) continue;
-                if (slot == 0) {
-                    x[0] = t0; x[1] = t1; x[2] = t2; x[3] = t3; x[4] = t4; x[5] = t5; x[6] = t6; x[7] = t7; y[0] = t8;
-                    j0 = j; slot = 1;
-                } else {
-                    x[8] = t0; x[9] = t1; x[10] = t2; x[11] = t3; x[12] = t4; x[13] = t5; x[14] = t6; x[15] = t7; y[1] = t8;
-                    j1 = j; slot = 2;
-                    flush();
-                }
             }
-        }
-        if (slot == 1) {
+            if (slot == 1) {
 #pragma unroll
-            for (int i = 8; i < 16; ++i) x[i] = 0.f;
-            y[1] = 0.f;
-            flush();
-        }
-        __syncthreads();  // stage s fully consumed -> may be refilled
-        if (tid == 0 && b + kStages < nbatch) issue(b + kStages);
-    }
-}
-
-// ---- v1 (kept for A/B timing only: GPSG_RENDER_IMPL=v1): no culling, per-Gaussian 9x5 shuffle reduction ------
-__global__ void __launch_bounds__(256) render_backward_v1_kernel(const __grid_constant__ Camera cam,
-                                                                 const float4* __restrict__ slabA,
-                                                                 const float4* __restrict__ slabB,
-                                                                 const float4* __restrict__ slabC,
-                                                                 const uint2* __restrict__ ranges,
-                                                                 const float* __restrict__ final_T,
-                                                                 const uint32_t* __restrict__ n_contrib,
-                                                                 const float* __restrict__ dL_dpix,
-                                                                 float* __restrict__ dL_dmeans2D,
-                                                                 float4* __restrict__ dL_dconic_op,
-                                                                 float* __restrict__ dL_dcolors) {
-    __shared__ float4 sA[GPSG_TILE_PIX];
-    __shared__ float4 sB[GPSG_TILE_PIX];
-    __shared__ float4 sC[GPSG_TILE_PIX];
-    const int tile = blockIdx.y * cam.grid_x + blockIdx.x;
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    const int px = blockIdx.x * GPSG_TILE_X + ((w & 1) << 3) + (l & 7), py = blockIdx.y * GPSG_TILE_Y + ((w >> 1) << 2) + (l >> 3);
-    const bool inside = px < cam.W && py < cam.H;
-    const float pixfx = (float)px, pixfy = (float)py;
-    const uint2 range = ranges[tile];
-    const int total = (int)(range.y - range.x);
-    const int rounds = (total + GPSG_TILE_PIX - 1) / GPSG_TILE_PIX;
-    const size_t HW = (size_t)cam.W * cam.H;
-    const size_t pid = (size_t)py * cam.W + px;
-    const float T_final = inside ? final_T[pid] : 0.0f;
-    float T = T_final;
-    uint32_t contributor = (uint32_t)total;
-    const uint32_t last_contributor = inside ? n_contrib[pid] : 0u;
-    float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f, lastc0 = 0.f, lastc1 = 0.f, lastc2 = 0.f, last_alpha = 0.f;
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-    if (inside) { g0 = dL_dpix[pid]; g1 = dL_dpix[HW + pid]; g2 = dL_dpix[2 * HW + pid]; }
-    const float bg_dot = (cam.bg[0] * g0 + cam.bg[1] * g1) + cam.bg[2] * g2;
-    const float ddelx_dx = 0.5f * (float)cam.W, ddely_dy = 0.5f * (float)cam.H;
-    int todo = total;
-    for (int r = 0; r < rounds; ++r, todo -= GPSG_TILE_PIX) {
-        __syncthreads();
-        const int n = min(GPSG_TILE_PIX, todo);
-        if ((int)threadIdx.x < n) {
-            const size_t k = (size_t)range.y - 1 - (size_t)r * GPSG_TILE_PIX - threadIdx.x;
-            sA[threadIdx.x] = slabA[k]; sB[threadIdx.x] = slabB[k]; sC[threadIdx.x] = slabC[k];
-        }
-        __syncthreads();
-        for (int j = 0; j < n; ++j) {
-            --contributor;
-            bool active = inside && contributor < last_contributor;
-            float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f, t5 = 0.f, t6 = 0.f, t7 = 0.f, t8 = 0.f;
-            if (active) {
-                const float4 a = sA[j];
-                const float4 q = sB[j];
-                const float dx = a.x - pixfx, dy = a.y - pixfy;
-                const float power = -0.5f * (q.x * dx * dx + q.z * dy * dy) - q.y * dx * dy;
-                const float G = __expf(power);
-                const float alpha = fminf(0.99f, q.w * G);
-                active = !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-                if (active) {
-                    const float4 c = sC[j];
-                    T = T / (1.0f - alpha);
-                    const float dchannel_dcolor = alpha * T;
-                    accum0 = last_alpha * lastc0 + (1.f - last_alpha) * accum0; lastc0 = c.x;
-                    accum1 = last_alpha * lastc1 + (1.f - last_alpha) * accum1; lastc1 = c.y;
-                    accum2 = last_alpha * lastc2 + (1.f - last_alpha) * accum2; lastc2 = c.z;
-                    float dL_dalpha = (c.x - accum0) * g0;
-                    dL_dalpha += (c.y - accum1) * g1;
-                    dL_dalpha += (c.z - accum2) * g2;
-                    t6 = dchannel_dcolor * g0; t7 = dchannel_dcolor * g1; t8 = dchannel_dcolor * g2;
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-                    const float dL_dG = q.w * dL_dalpha;
-                    const float gdx = G * dx, gdy = G * dy;
-                    t0 = dL_dG * (-gdx * q.x - gdy * q.y) * ddelx_dx;
-                    t1 = dL_dG * (-gdy * q.z - gdx * q.y) * ddely_dy;
-                    t2 = -0.5f * gdx * dx * dL_dG; t3 = -0.5f * gdx * dy * dL_dG; t4 = -0.5f * gdy * dy * dL_dG;
-                    t5 = G * dL_dalpha;
-                }
-            }
-            if (!__any_sync(0xffffffffu, active)) continue;
-            t0 = warp_sum(t0); t1 = warp_sum(t1); t2 = warp_sum(t2); t3 = warp_sum(t3); t4 = warp_sum(t4);
-            t5 = warp_sum(t5); t6 = warp_sum(t6); t7 = warp_sum(t7); t8 = warp_sum(t8);
-            if (l == 0) {
-                const uint32_t id = __float_as_uint(sC[j].w);
-                atomicAdd(&dL_dmeans2D[3 * id], t0); atomicAdd(&dL_dmeans2D[3 * id + 1], t1);
-                float* co = reinterpret_cast<float*>(&dL_dconic_op[id]);
-                atomicAdd(co, t2); atomicAdd(co + 1, t3); atomicAdd(co + 2, t4); atomicAdd(co + 3, t5);
-                atomicAdd(&dL_dcolors[3 * id], t6); atomicAdd(&dL_dcolors[3 * id + 1], t7); atomicAdd(&dL_dcolors[3 * id + 2], t8);
+                for (int i = 8; i < 16; ++i) x[i] = 0.f;
+                y[1] = 0.f;
+                flush();
             }
         }
+        ring_release(ring, b, lane);
     }
 }
 
 int launch_render_backward(const Camera& cam, BinningState b, ImageState im, const float* dL_dpix, float* dL_dmeans2D,
                            float4* dL_dconic_op, float* dL_dcolors, cudaStream_t stream) {
-    dim3 grid(cam.grid_x, cam.grid_y);
-    if (use_v1_kernels())
-        render_backward_v1_kernel<<<grid, GPSG_TILE_PIX, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges,
+    dim3 grid(cam.grid_x, cam.grid_y * 2);
+    render_backward_kernel<<<grid, (kBwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges,
                                                                      im.final_T, im.n_contrib, dL_dpix, dL_dmeans2D,
                                                                      dL_dconic_op, dL_dcolors);
-    else
-        render_backward_kernel<<<grid, GPSG_TILE_PIX, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges, im.final_T,
-                                                                  im.n_contrib, dL_dpix, dL_dmeans2D, dL_dconic_op,
-                                                                  dL_dcolors);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
 }

@@ -106,7 +106,9 @@ __global__ void __launch_bounds__(256) gather_ranges_kernel(size_t N, const floa
         if (!(ex == ex) || !(ey == ey)) { ex = 3.0e38f; ey = 3.0e38f; }
     }
     b.slabA[i] = make_float4(xy.x, xy.y, ex, ey);
-    b.slabB[i] = make_float4(co.x, co.y, co.z, co.w);
+    // conic pre-scaled into the log2 domain: alpha = o * 2^(Bx dx^2 + By dx dy + Bz dy^2)
+    const float kL = 1.4426950408889634f;
+    b.slabB[i] = make_float4(-0.5f * kL * co.x, -kL * co.y, -0.5f * kL * co.z, co.w);
     b.slabC[i] = make_float4(r, gg, bb, __uint_as_float(id));
 }
 
