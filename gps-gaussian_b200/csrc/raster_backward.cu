@@ -6,8 +6,8 @@
 
 namespace gpsg {
 
-constexpr int kBwdChunk = 128;  // Gaussians per ring stage
-constexpr int kBwdStages = 4;
+constexpr int kBwdChunk = 64;   // Gaussians per ring stage
+constexpr int kBwdStages = 8;
 constexpr int kBwdWarps = 4;    // consumer warps per CTA: 16 x 8 pixels (half a tile)
 
 // One butterfly exchange step of a reduce-scatter: halves the number of live values per lane.
@@ -96,34 +96,49 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32) render_backward_kernel(c
             const float4* __restrict__ SA = ring.A[s];
             const float4* __restrict__ SB = ring.B[s];
             const float4* __restrict__ SC = ring.C[s];
-            // two pending Gaussians: x[0..7]/x[8..15] = comps (dmx,dmy,dcx,dcy,dcw,dop,dr,dg), y[0..1] = db
-            float x[16], y[2];
-            int j0 = 0, j1 = 0, slot = 0;
-            auto flush = [&]() {
-                rs_step<16>(x, lane, 16);
-                rs_step<8>(x, lane, 8);
-                rs_step<4>(x, lane, 4);
-                rs_step<2>(x, lane, 2);
-                const float tot = x[0] + __shfl_xor_sync(0xffffffffu, x[0], 1);  // lane l holds total of value l>>1
-                rs_step<2>(y, lane, 16);
-                float tb = y[0];
-                tb += __shfl_xor_sync(0xffffffffu, tb, 8);
-                tb += __shfl_xor_sync(0xffffffffu, tb, 4);
-                tb += __shfl_xor_sync(0xffffffffu, tb, 2);
-                tb += __shfl_xor_sync(0xffffffffu, tb, 1);                       // lanes 0-15: Gaussian 0, 16-31: Gaussian 1
-                const int gsel = lane >> 4;
-                if (gsel < slot) {
-                    const uint32_t id = __float_as_uint(SC[gsel ? j1 : j0].w);
-                    if ((lane & 1) == 0) {
-                        const int k = (lane >> 1) & 7;
-                        float* dst = (k < 2) ? (dL_dmeans2D + 3 * (size_t)id + k)
-                                             : (k < 6) ? (reinterpret_cast<float*>(dL_dconic_op + id) + (k - 2))
-                                                       : (dL_dcolors + 3 * (size_t)id + (k - 6));
-                        atomicAdd(dst, tot);
+            // Survivors are taken two at a time (deeper one first): their 2 x 9 per-pixel gradient terms go straight
+            // into x[0..7]/x[8..15] (dmx,dmy,dcx,dcy,dcw,dop,dr,dg) and y[0..1] (db), then one butterfly per pair.
+            auto eval = [&](int j, float* xo, float& yo) -> bool {
+                bool active = (start + j) < last_contributor;   // implies inside
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xo[i] = 0.f;
+                yo = 0.f;
+                if (active) {
+                    const float2 xy = *reinterpret_cast<const float2*>(&SA[j]);
+                    const float4 q = SB[j];
+                    const float dx = xy.x - pixfx, dy = xy.y - pixfy;
+                    const float p = fmaf(q.z * dy, dy, fmaf(q.x, dx, q.y * dy) * dx);   // log2e * power
+                    const float G = ex2_approx(p);
+                    const float alpha = fminf(0.99f, q.w * G);
+                    active = !(p > 0.0f) && !(alpha < 1.0f / 255.0f);
+                    if (active) {
+                        const float4 c = SC[j];
+                        const float inv1ma = __frcp_rn(1.0f - alpha);
+                        T = T * inv1ma;
+                        const float dchannel_dcolor = alpha * T;
+                        accum0 = fmaf(last_alpha, lastc0 - accum0, accum0); lastc0 = c.x;
+                        accum1 = fmaf(last_alpha, lastc1 - accum1, accum1); lastc1 = c.y;
+                        accum2 = fmaf(last_alpha, lastc2 - accum2, accum2); lastc2 = c.z;
+                        float dL_dalpha = (c.x - accum0) * g0;
+                        dL_dalpha = fmaf(c.y - accum1, g1, dL_dalpha);
+                        dL_dalpha = fmaf(c.z - accum2, g2, dL_dalpha);
+                        xo[6] = dchannel_dcolor * g0; xo[7] = dchannel_dcolor * g1; yo = dchannel_dcolor * g2;
+                        dL_dalpha *= T;
+                        last_alpha = alpha;
+                        dL_dalpha = fmaf(-T_final * inv1ma, bg_dot, dL_dalpha);
+                        const float dL_dG = q.w * dL_dalpha;
+                        // conic = (-2 ln2 Bx, -ln2 By, -2 ln2 Bz): dG/ddelx = -G (cx dx + cy dy) = ln2 G (2 Bx dx + By dy)
+                        const float gl = kLn2 * G * dL_dG;
+                        xo[0] = gl * fmaf(2.0f * q.x, dx, q.y * dy) * ddelx_dx;
+                        xo[1] = gl * fmaf(2.0f * q.z, dy, q.y * dx) * ddely_dy;
+                        const float h = -0.5f * G * dL_dG;
+                        xo[2] = h * dx * dx;
+                        xo[3] = h * dx * dy;
+                        xo[4] = h * dy * dy;
+                        xo[5] = G * dL_dalpha;
                     }
-                    if ((lane & 15) == 1) atomicAdd(dL_dcolors + 3 * (size_t)id + 2, tb);
                 }
-                slot = 0;
+                return active;
             };
             for (int base = ((n - 1) >> 5) << 5; base >= 0; base -= 32) {
                 if (start + base >= wmax) continue;
@@ -135,62 +150,48 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32) render_backward_kernel(c
                 }
                 unsigned m = __ballot_sync(0xffffffffu, hit);
                 while (m) {
-                    const int bit = 31 - __clz(m);
-                    m &= ~(1u << bit);
-                    const int j = base + bit;
-                    bool active = (start + j) < last_contributor;   // implies inside
-                    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f, t5 = 0.f, t6 = 0.f, t7 = 0.f, t8 = 0.f;
-                    if (active) {
-                        const float2 xy = *reinterpret_cast<const float2*>(&SA[j]);
-                        const float4 q = SB[j];
-                        const float dx = xy.x - pixfx, dy = xy.y - pixfy;
-                        const float p = fmaf(q.z * dy, dy, fmaf(q.x, dx, q.y * dy) * dx);   // log2e * power
-                        const float G = ex2_approx(p);
-                        const float alpha = fminf(0.99f, q.w * G);
-                        active = !(p > 0.0f) && !(alpha < 1.0f / 255.0f);
-                        if (active) {
-                            const float4 c = SC[j];
-                            const float inv1ma = __frcp_rn(1.0f - alpha);
-                            T = T * inv1ma;
-                            const float dchannel_dcolor = alpha * T;
-                            accum0 = last_alpha * lastc0 + (1.f - last_alpha) * accum0; lastc0 = c.x;
-                            accum1 = last_alpha * lastc1 + (1.f - last_alpha) * accum1; lastc1 = c.y;
-                            accum2 = last_alpha * lastc2 + (1.f - last_alpha) * accum2; lastc2 = c.z;
-                            float dL_dalpha = (c.x - accum0) * g0;
-                            dL_dalpha += (c.y - accum1) * g1;
-                            dL_dalpha += (c.z - accum2) * g2;
-                            t6 = dchannel_dcolor * g0; t7 = dchannel_dcolor * g1; t8 = dchannel_dcolor * g2;
-                            dL_dalpha *= T;
-                            last_alpha = alpha;
-                            dL_dalpha = fmaf(-T_final * inv1ma, bg_dot, dL_dalpha);
-                            const float dL_dG = q.w * dL_dalpha;
-                            // conic = (-2 ln2 Bx, -ln2 By, -2 ln2 Bz): dG/ddelx = -G (cx dx + cy dy) = ln2 G (2 Bx dx + By dy)
-                            const float gl = kLn2 * G * dL_dG;
-                            t0 = gl * fmaf(2.0f * q.x, dx, q.y * dy) * ddelx_dx;
-                            t1 = gl * fmaf(2.0f * q.z, dy, q.y * dx) * ddely_dy;
-                            const float h = -0.5f * G * dL_dG;
-                            t2 = h * dx * dx;
-                            t3 = h * dx * dy;
-                            t4 = h * dy * dy;
-                            t5 = G * dL_dalpha;
-                        }
-                    }
-                    if (!__any_sync(0xffffffffu, active)) continue;
-                    if (slot == 0) {
-                        x[0] = t0; x[1] = t1; x[2] = t2; x[3] = t3; x[4] = t4; x[5] = t5; x[6] = t6; x[7] = t7; y[0] = t8;
-                        j0 = j; slot = 1;
+                    float x[16], y[2];
+                    const int bitA = 31 - __clz(m);
+                    m &= ~(1u << bitA);
+                    const int jA = base + bitA;
+                    bool act = eval(jA, x, y[0]);
+                    int jB = jA;
+                    const bool two = m != 0;
+                    if (two) {
+                        const int bitB = 31 - __clz(m);
+                        m &= ~(1u << bitB);
+                        jB = base + bitB;
+                        act |= eval(jB, x + 8, y[1]);
                     } else {
-                        x[8] = t0; x[9] = t1; x[10] = t2; x[11] = t3; x[12] = t4; x[13] = t5; x[14] = t6; x[15] = t7; y[1] = t8;
-                        j1 = j; slot = 2;
-                        flush();
+#pragma unroll
+                        for (int i = 8; i < 16; ++i) x[i] = 0.f;
+                        y[1] = 0.f;
+                    }
+                    if (!__any_sync(0xffffffffu, act)) continue;
+                    rs_step<16>(x, lane, 16);
+                    rs_step<8>(x, lane, 8);
+                    rs_step<4>(x, lane, 4);
+                    rs_step<2>(x, lane, 2);
+                    const float tot = x[0] + __shfl_xor_sync(0xffffffffu, x[0], 1);  // lane l holds total of value l>>1
+                    rs_step<2>(y, lane, 16);
+                    float tb = y[0];
+                    tb += __shfl_xor_sync(0xffffffffu, tb, 8);
+                    tb += __shfl_xor_sync(0xffffffffu, tb, 4);
+                    tb += __shfl_xor_sync(0xffffffffu, tb, 2);
+                    tb += __shfl_xor_sync(0xffffffffu, tb, 1);                       // lanes 0-15: first, 16-31: second
+                    const int gsel = lane >> 4;
+                    if (gsel == 0 || two) {
+                        const uint32_t id = __float_as_uint(SC[gsel ? jB : jA].w);
+                        if ((lane & 1) == 0 && tot != 0.0f) {
+                            const int k = (lane >> 1) & 7;
+                            float* dst = (k < 2) ? (dL_dmeans2D + 3 * (size_t)id + k)
+                                                 : (k < 6) ? (reinterpret_cast<float*>(dL_dconic_op + id) + (k - 2))
+                                                           : (dL_dcolors + 3 * (size_t)id + (k - 6));
+                            atomicAdd(dst, tot);
+                        }
+                        if ((lane & 15) == 1 && tb != 0.0f) atomicAdd(dL_dcolors + 3 * (size_t)id + 2, tb);
                     }
                 }
-            }
-            if (slot == 1) {
-#pragma unroll
-                for (int i = 8; i < 16; ++i) x[i] = 0.f;
-                y[1] = 0.f;
-                flush();
             }
         }
         ring_release(ring, b, lane);

@@ -17,8 +17,8 @@
 
 namespace gpsg {
 
-constexpr int kFwdChunk = 128;  // Gaussians per ring stage (3 x 2 KB)
-constexpr int kFwdStages = 4;
+constexpr int kFwdChunk = 64;   // Gaussians per ring stage (3 x 1 KB)
+constexpr int kFwdStages = 8;
 constexpr int kFwdWarps = 4;    // consumer warps per CTA: 16 x 8 pixels
 
 __global__ void __launch_bounds__((kFwdWarps + 1) * 32) render_forward_kernel(const __grid_constant__ Camera cam,

@@ -55,8 +55,15 @@ __device__ __forceinline__ void ring_produce(SlabRing<CHUNK, STAGES>& r, int nba
     int issued = 0;
     for (int b = 0; b < nbatch; ++b) {
         const int s = b % STAGES;
-        if (b >= STAGES) mbar_wait(&r.empty[s], (uint32_t)(((b / STAGES) - 1) & 1));
-        if (*(volatile int*)&r.done_warps >= consumer_warps) break;
+        bool stop = false;
+        if (b >= STAGES) {
+            const uint32_t par = (uint32_t)(((b / STAGES) - 1) & 1);
+            while (!mbar_try_wait(&r.empty[s], par)) {   // consumers that are all done stop arriving: poll the flag
+                if (*(volatile int*)&r.done_warps >= consumer_warps) { stop = true; break; }
+                __nanosleep(128);                        // ncu: a hot spin here cost ~20% of the SM's issue slots
+            }
+        }
+        if (stop || *(volatile int*)&r.done_warps >= consumer_warps) break;
         const uint32_t bytes = (uint32_t)count(b) * 16u;
         const size_t k = first(b);
         mbar_expect_tx(&r.full[s], 3u * bytes);
@@ -66,7 +73,8 @@ __device__ __forceinline__ void ring_produce(SlabRing<CHUNK, STAGES>& r, int nba
         issued = b + 1;
     }
     // a bulk copy must not be in flight into this CTA's shared memory when the CTA retires
-    for (int b = max(0, issued - STAGES); b < issued; ++b) mbar_wait(&r.full[b % STAGES], (uint32_t)((b / STAGES) & 1));
+    for (int b = max(0, issued - STAGES); b < issued; ++b)
+        while (!mbar_try_wait(&r.full[b % STAGES], (uint32_t)((b / STAGES) & 1))) __nanosleep(64);
 }
 
 // Consumer side: wait for batch b; returns false if every consumer warp is done (nothing more will arrive).
