@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "gpsg_internal.cuh"
 
 namespace gpsg {
@@ -75,6 +76,7 @@ static BinningState carve_binning(char* p, size_t N, size_t sort_bytes, char** e
     b.keys = take<uint64_t>(p, n);
     b.vals = take<uint32_t>(p, n);
     b.keys_unsorted = take<uint64_t>(p, n);
+    b.bucket = reinterpret_cast<uint2*>(b.keys_unsorted);   // tile-bucket path: same bytes, never both in use
     b.vals_unsorted = take<uint32_t>(p, n);
     b.sort_temp = p;
     b.sort_temp_bytes = sort_bytes;
@@ -98,6 +100,9 @@ static ImageState carve_image(char* p, int W, int H, char** end) {
     im.final_T = take<float>(p, hw > 0 ? hw : 1);
     im.n_contrib = take<uint32_t>(p, hw > 0 ? hw : 1);
     im.ranges = take<uint2>(p, tiles > 0 ? tiles : 1);
+    im.tile_count = take<uint32_t>(p, tiles > 0 ? tiles : 1);
+    im.tile_cursor = take<uint32_t>(p, tiles > 0 ? tiles : 1);
+    im.totals = take<uint32_t>(p, 64);
     if (end) *end = p;
     return im;
 }
@@ -112,6 +117,11 @@ static int bit_length(uint32_t n) {
     int b = 0;
     while (n) { ++b; n >>= 1; }
     return b;
+}
+
+static bool force_radix_binning() {
+    static const bool v = [] { const char* e = getenv("GPSG_BINNING"); return e && e[0] == 'r'; }();
+    return v;
 }
 
 // pinned host slot for the one device->host read of the forward (num_rendered)
@@ -137,7 +147,8 @@ struct Profiler {
     int launches[ST_COUNT] = {0};
 };
 static thread_local Profiler g_prof;
-static const char* kStageNames[ST_COUNT] = {"preprocess", "scan", "duplicate", "sort", "gather_ranges", "render_forward",
+static const char* kStageNames[ST_COUNT] = {"preprocess", "scan", "duplicate", "sort", "gather_ranges", "tile_scan",
+                                            "bucket_scatter", "tile_sort_gather", "render_forward",
                                             "render_backward", "preprocess_backward", "corr_forward", "corr_backward"};
 StageTimer::StageTimer(Stage s, cudaStream_t st, int launches) : stage(s), stream(st), slot(nullptr) {
     if (!g_prof.on) return;
@@ -193,40 +204,55 @@ int gpsg_rasterize_forward(const GpsgRasterSettings* s, int device, void* stream
     void* geom_base = geom_alloc(geom_user, GeomState::required(P, scan_bytes));
     if (!geom_base) { set_error("geometry allocator returned NULL"); return GPSG_E_ALLOC; }
     GeomState g = GeomState::carve(geom_base, P, scan_bytes);
-
-    uint32_t N = 0;
-    if (P > 0) {
-        int rc;
-        { StageTimer t(ST_PREPROCESS, stream, 1); rc = launch_preprocess(cam, P, means3D, scales, rotations, opacities, cov3D_precomp, radii, g, stream); }
-        if (rc) return rc;
-        { StageTimer t(ST_SCAN, stream, 2); rc = run_scan(g, P, stream); }
-        if (rc) return rc;
-        uint32_t* slot = pinned_slot();
-        GPSG_REQUIRE(slot != nullptr, "cudaHostAlloc failed");
-        GPSG_CUDA(cudaMemcpyAsync(slot, g.point_offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-        GPSG_CUDA(cudaStreamSynchronize(stream));
-        N = *slot;
-    }
-    if (num_rendered) *num_rendered = (int32_t)N;
-
-    const int end_bit = 32 + bit_length((uint32_t)(cam.grid_x * cam.grid_y));
-    const size_t sort_bytes = sort_temp_bytes(N, end_bit);
-    void* bin_base = binning_alloc(binning_user, BinningState::required(N, sort_bytes));
-    if (!bin_base) { set_error("binning allocator returned NULL"); return GPSG_E_ALLOC; }
-    BinningState b = BinningState::carve(bin_base, N, sort_bytes);
     void* img_base = image_alloc(image_user, ImageState::required(cam.W, cam.H));
     if (!img_base) { set_error("image allocator returned NULL"); return GPSG_E_ALLOC; }
     ImageState im = ImageState::carve(img_base, cam.W, cam.H);
+    const int tiles = cam.grid_x * cam.grid_y;
 
+    // ---- per-Gaussian projection + pairs-per-tile counts, then tile ranges; one host read: (N, max tile count)
+    uint32_t N = 0, max_count = 0;
     int rc = GPSG_OK;
-    if (N > 0) {
+    GPSG_CUDA(cudaMemsetAsync(im.tile_count, 0, sizeof(uint32_t) * (size_t)tiles, stream));
+    if (P > 0) {
+        { StageTimer t(ST_PREPROCESS, stream, 1); rc = launch_preprocess(cam, P, means3D, scales, rotations, opacities, cov3D_precomp, radii, g, im.tile_count, stream); }
+        if (rc) return rc;
+    }
+    { StageTimer t(ST_TILE_SCAN, stream, 1); rc = launch_tile_scan(cam, im, stream); }
+    if (rc) return rc;
+    if (P > 0) {
+        uint32_t* slot = pinned_slot();
+        GPSG_REQUIRE(slot != nullptr, "cudaHostAlloc failed");
+        GPSG_CUDA(cudaMemcpyAsync(slot, im.totals, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        GPSG_CUDA(cudaStreamSynchronize(stream));
+        N = slot[0];
+        max_count = slot[1];
+    }
+    if (num_rendered) *num_rendered = (int32_t)N;
+
+    const bool radix_path = max_count > kMaxTileSort || force_radix_binning();
+    const int end_bit = 32 + bit_length((uint32_t)tiles);
+    const size_t sort_bytes = radix_path ? sort_temp_bytes(N, end_bit) : 0;
+    void* bin_base = binning_alloc(binning_user, BinningState::required(N, sort_bytes));
+    if (!bin_base) { set_error("binning allocator returned NULL"); return GPSG_E_ALLOC; }
+    BinningState b = BinningState::carve(bin_base, N, sort_bytes);
+
+    if (N > 0 && !radix_path) {
+        // tile-bucket binning: scatter into per-tile buckets, sort each tile inside one CTA, gather slabs
+        { StageTimer t(ST_SCATTER, stream, 1); rc = launch_bucket_scatter(cam, P, radii, g, b, im, stream); }
+        if (rc) return rc;
+        { StageTimer t(ST_TILE_SORT, stream, 1); rc = launch_tile_sort_gather(cam, max_count, colors_precomp, g, b, im, stream); }
+        if (rc) return rc;
+    } else if (N > 0) {
+        // fallback (a tile list too long for the in-CTA sort, or GPSG_BINNING=radix): upstream-style global radix sort
+        { StageTimer t(ST_SCAN, stream, 2); rc = run_scan(g, P, stream); }
+        if (rc) return rc;
         { StageTimer t(ST_DUPLICATE, stream, 1); rc = launch_duplicate(cam, P, radii, g, b, stream); }
         if (rc) return rc;
         { StageTimer t(ST_SORT, stream, 2 + (end_bit + 7) / 8); rc = run_sort(b, N, end_bit, stream); }
         if (rc) return rc;
+        { StageTimer t(ST_GATHER, stream, 1); rc = launch_gather_ranges(cam, N, colors_precomp, g, b, im, stream); }
+        if (rc) return rc;
     }
-    { StageTimer t(ST_GATHER, stream, N > 0 ? 1 : 0); rc = launch_gather_ranges(cam, N, colors_precomp, g, b, im, stream); }
-    if (rc) return rc;
     { StageTimer t(ST_RENDER_FWD, stream, 1); rc = launch_render_forward(cam, b, im, out_color, stream); }
     if (rc) return rc;
     if (s->debug) GPSG_CUDA(cudaStreamSynchronize(stream));

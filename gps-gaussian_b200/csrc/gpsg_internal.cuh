@@ -59,6 +59,7 @@ struct GeomState {
     static GeomState carve(void* base, int P, size_t scan_temp_bytes);
 };
 struct BinningState {
+    uint2* bucket;            // [N] tile-bucketed (depth bits, id), unordered inside a tile (aliases keys_unsorted)
     uint64_t* keys_unsorted;  // [N]
     uint32_t* vals_unsorted;  // [N]
     uint64_t* keys;           // [N] sorted (tile<<32 | depth bits)
@@ -75,6 +76,9 @@ struct ImageState {
     float* final_T;       // [HW]
     uint32_t* n_contrib;  // [HW]
     uint2* ranges;        // [tiles]
+    uint32_t* tile_count; // [tiles]  pairs per tile (counted by preprocess)
+    uint32_t* tile_cursor;// [tiles]  scatter cursors
+    uint32_t* totals;     // [2]      (N = sum of counts, max count)
     static size_t required(int W, int H);
     static ImageState carve(void* base, int W, int H);
 };
@@ -85,7 +89,7 @@ size_t sort_temp_bytes(size_t N, int end_bit);
 // raster_preprocess.cu  (compiled with -fmad=false: integer outputs follow the oracle's op order)
 int launch_preprocess(const Camera& cam, int P, const float* means3D, const float* scales, const float* rots,
                       const float* opacities, const float* cov3D_precomp, int32_t* radii, GeomState g,
-                      cudaStream_t stream);
+                      uint32_t* tile_count, cudaStream_t stream);
 int launch_mark_visible(int P, const float* means3D, const float* view16_host, uint8_t* present, cudaStream_t stream);
 // raster_binning.cu
 int run_scan(GeomState g, int P, cudaStream_t stream);
@@ -93,6 +97,13 @@ int launch_duplicate(const Camera& cam, int P, const int32_t* radii, GeomState g
 int run_sort(BinningState b, size_t N, int end_bit, cudaStream_t stream);
 int launch_gather_ranges(const Camera& cam, size_t N, const float* colors, GeomState g, BinningState b, ImageState im,
                          cudaStream_t stream);
+// tile-bucket path (default): counts -> ranges, bucket scatter, per-tile in-CTA sort fused with the slab gather
+constexpr uint32_t kMaxTileSort = 8192;  // largest tile list the in-CTA sort handles (64 KB smem); beyond: radix path
+int launch_tile_scan(const Camera& cam, ImageState im, cudaStream_t stream);
+int launch_bucket_scatter(const Camera& cam, int P, const int32_t* radii, GeomState g, BinningState b, ImageState im,
+                          cudaStream_t stream);
+int launch_tile_sort_gather(const Camera& cam, uint32_t max_count, const float* colors, GeomState g, BinningState b,
+                            ImageState im, cudaStream_t stream);
 // raster_render.cu
 int launch_render_forward(const Camera& cam, BinningState b, ImageState im, float* out_color, cudaStream_t stream);
 // raster_backward.cu
@@ -112,7 +123,7 @@ int launch_corr_bwd(int dtype, int B, int H, int W1, int W2, const float* coords
 
 
 // ---- optional per-stage timing (bench.py); see gpsg_profile_* in gpsg.h ---------------------
-enum Stage { ST_PREPROCESS = 0, ST_SCAN, ST_DUPLICATE, ST_SORT, ST_GATHER, ST_RENDER_FWD, ST_RENDER_BWD,
+enum Stage { ST_PREPROCESS = 0, ST_SCAN, ST_DUPLICATE, ST_SORT, ST_GATHER, ST_TILE_SCAN, ST_SCATTER, ST_TILE_SORT, ST_RENDER_FWD, ST_RENDER_BWD,
              ST_PREPROCESS_BWD, ST_CORR_FWD, ST_CORR_BWD, ST_COUNT };
 struct StageTimer {  // RAII: records begin/end events on `stream` when profiling is on
     StageTimer(Stage s, cudaStream_t stream, int launches);

@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
                                                          const float* __restrict__ rots,
                                                          const float* __restrict__ opacities,
                                                          const float* __restrict__ cov3D_precomp,
-                                                         int32_t* __restrict__ radii, GeomState g) {
+                                                         int32_t* __restrict__ radii, GeomState g,
+                                                         uint32_t* __restrict__ tile_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     int32_t out_radius = 0;
@@ -109,6 +110,9 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
         g.conic_opacity[i] = make_float4(conx, cony, conz, opacities[i]);
         out_radius = my_radius;
         out_tiles = (uint32_t)area;
+        if (tile_count)  // tile-bucket binning: pairs per tile (sizes the buckets, replaces the per-Gaussian scan)
+            for (int tile_y = ry0; tile_y < ry1; ++tile_y)
+                for (int tile_x = rx0; tile_x < rx1; ++tile_x) atomicAdd(&tile_count[tile_y * cam.grid_x + tile_x], 1u);
     } while (0);
     radii[i] = out_radius;
     g.tiles_touched[i] = out_tiles;
@@ -116,10 +120,10 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
 
 int launch_preprocess(const Camera& cam, int P, const float* means3D, const float* scales, const float* rots,
                       const float* opacities, const float* cov3D_precomp, int32_t* radii, GeomState g,
-                      cudaStream_t stream) {
+                      uint32_t* tile_count, cudaStream_t stream) {
     if (P <= 0) return GPSG_OK;
     preprocess_kernel<<<(P + 255) / 256, 256, 0, stream>>>(cam, P, means3D, scales, rots, opacities, cov3D_precomp,
-                                                          radii, g);
+                                                          radii, g, tile_count);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
 }
