@@ -240,7 +240,7 @@ int gpsg_rasterize_forward(const GpsgRasterSettings* s, int device, void* stream
         // tile-bucket binning: scatter into per-tile buckets, sort each tile inside one CTA, gather slabs
         { StageTimer t(ST_SCATTER, stream, 1); rc = launch_bucket_scatter(cam, P, radii, g, b, im, stream); }
         if (rc) return rc;
-        { StageTimer t(ST_TILE_SORT, stream, 1); rc = launch_tile_sort_gather(cam, max_count, colors_precomp, g, b, im, stream); }
+        { StageTimer t(ST_TILE_SORT, stream, max_count > 2048 ? 2 : 1); rc = launch_tile_sort_gather(cam, P, max_count, colors_precomp, g, b, im, stream); }
         if (rc) return rc;
     } else if (N > 0) {
         // fallback (a tile list too long for the in-CTA sort, or GPSG_BINNING=radix): upstream-style global radix sort

@@ -98,12 +98,12 @@ int run_sort(BinningState b, size_t N, int end_bit, cudaStream_t stream);
 int launch_gather_ranges(const Camera& cam, size_t N, const float* colors, GeomState g, BinningState b, ImageState im,
                          cudaStream_t stream);
 // tile-bucket path (default): counts -> ranges, bucket scatter, per-tile in-CTA sort fused with the slab gather
-constexpr uint32_t kMaxTileSort = 8192;  // largest tile list the in-CTA sort handles (64 KB smem); beyond: radix path
+constexpr uint32_t kMaxTileSort = 4096;  // largest tile list the in-CTA sort handles (256 thr x 16 keys); beyond: radix path
 int launch_tile_scan(const Camera& cam, ImageState im, cudaStream_t stream);
 int launch_bucket_scatter(const Camera& cam, int P, const int32_t* radii, GeomState g, BinningState b, ImageState im,
                           cudaStream_t stream);
-int launch_tile_sort_gather(const Camera& cam, uint32_t max_count, const float* colors, GeomState g, BinningState b,
-                            ImageState im, cudaStream_t stream);
+int launch_tile_sort_gather(const Camera& cam, int P, uint32_t max_count, const float* colors, GeomState g,
+                            BinningState b, ImageState im, cudaStream_t stream);
 // raster_render.cu
 int launch_render_forward(const Camera& cam, BinningState b, ImageState im, float* out_color, cudaStream_t stream);
 // raster_backward.cu

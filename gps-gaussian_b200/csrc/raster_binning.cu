@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, ImageState i
         __syncthreads();
         const uint32_t incl = v + (warp ? warp_sums[warp - 1] : 0u) + carry;
         if (t < tiles) {
-            im.ranges[t] = make_uint2(incl - c, incl);
+            im.ranges[t] = c ? make_uint2(incl - c, incl) : make_uint2(0u, 0u);   // empty tiles stay (0,0) as upstream
             im.tile_cursor[t] = 0u;
         }
         __syncthreads();
@@ -131,33 +131,67 @@ int launch_tile_scan(const Camera& cam, ImageState im, cudaStream_t stream) {
     return GPSG_OK;
 }
 
-// one thread per Gaussian: claims a slot in each touched tile's bucket and writes (depth bits, id)
+// one thread per Gaussian: claims a slot in each touched tile's bucket and writes (depth bits, id).
+// Slots are claimed in two levels: a CTA-local rank from a shared-memory counter, plus one global atomic per
+// (CTA, touched tile) for the CTA's base inside the bucket.  Order inside a bucket is irrelevant (sorted next).
 __global__ void __launch_bounds__(256) bucket_scatter_kernel(const __grid_constant__ Camera cam, int P,
                                                              const int32_t* __restrict__ radii, GeomState g,
-                                                             BinningState b, ImageState im) {
+                                                             BinningState b, ImageState im, int smem_hist) {
+    extern __shared__ uint32_t sh[];            // [tiles] local counts, then [tiles] CTA bases
+    const int tiles = cam.grid_x * cam.grid_y;
+    uint32_t* sh_cnt = sh;
+    uint32_t* sh_base = sh + tiles;
+    if (smem_hist) {
+        for (int t = threadIdx.x; t < tiles; t += blockDim.x) sh_cnt[t] = 0u;
+        __syncthreads();
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    const int radius = radii[i];
-    if (radius <= 0) return;
-    const float2 p = g.means2D[i];
-    const float rad = (float)radius;
-    const int rx0 = min(cam.grid_x, max(0, (int)((p.x - rad) / (float)GPSG_TILE_X)));
-    const int ry0 = min(cam.grid_y, max(0, (int)((p.y - rad) / (float)GPSG_TILE_Y)));
-    const int rx1 = min(cam.grid_x, max(0, (int)((p.x + rad + (float)(GPSG_TILE_X - 1)) / (float)GPSG_TILE_X)));
-    const int ry1 = min(cam.grid_y, max(0, (int)((p.y + rad + (float)(GPSG_TILE_Y - 1)) / (float)GPSG_TILE_Y)));
-    const uint2 entry = make_uint2((uint32_t)i, __float_as_uint(g.depths[i]));   // little-endian u64 = depth<<32 | id
+    int rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;
+    uint2 entry = make_uint2(0u, 0u);
+    if (i < P) {
+        const int radius = radii[i];
+        if (radius > 0) {
+            const float2 p = g.means2D[i];
+            const float rad = (float)radius;
+            rx0 = min(cam.grid_x, max(0, (int)((p.x - rad) / (float)GPSG_TILE_X)));
+            ry0 = min(cam.grid_y, max(0, (int)((p.y - rad) / (float)GPSG_TILE_Y)));
+            rx1 = min(cam.grid_x, max(0, (int)((p.x + rad + (float)(GPSG_TILE_X - 1)) / (float)GPSG_TILE_X)));
+            ry1 = min(cam.grid_y, max(0, (int)((p.y + rad + (float)(GPSG_TILE_Y - 1)) / (float)GPSG_TILE_Y)));
+            entry = make_uint2((uint32_t)i, __float_as_uint(g.depths[i]));   // little-endian u64 = depth<<32 | id
+        }
+    }
+    if (!smem_hist) {   // huge tile grids: one global atomic per pair
+        for (int y = ry0; y < ry1; ++y)
+            for (int x = rx0; x < rx1; ++x) {
+                const int t = y * cam.grid_x + x;
+                b.bucket[im.ranges[t].x + atomicAdd(&im.tile_cursor[t], 1u)] = entry;
+            }
+        return;
+    }
+    for (int y = ry0; y < ry1; ++y)
+        for (int x = rx0; x < rx1; ++x) atomicAdd(&sh_cnt[y * cam.grid_x + x], 1u);
+    __syncthreads();
+    for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+        const uint32_t c = sh_cnt[t];
+        if (c) {
+            sh_base[t] = im.ranges[t].x + atomicAdd(&im.tile_cursor[t], c);
+            sh_cnt[t] = 0u;
+        }
+    }
+    __syncthreads();
     for (int y = ry0; y < ry1; ++y)
         for (int x = rx0; x < rx1; ++x) {
             const int t = y * cam.grid_x + x;
-            const uint32_t pos = atomicAdd(&im.tile_cursor[t], 1u);
-            b.bucket[im.ranges[t].x + pos] = entry;
+            b.bucket[sh_base[t] + atomicAdd(&sh_cnt[t], 1u)] = entry;
         }
 }
 
 int launch_bucket_scatter(const Camera& cam, int P, const int32_t* radii, GeomState g, BinningState b, ImageState im,
                           cudaStream_t stream) {
     if (P <= 0) return GPSG_OK;
-    bucket_scatter_kernel<<<(P + 255) / 256, 256, 0, stream>>>(cam, P, radii, g, b, im);
+    const size_t bytes = 2 * sizeof(uint32_t) * (size_t)cam.grid_x * cam.grid_y;
+    const int smem_hist = bytes <= 48 * 1024 ? 1 : 0;
+    bucket_scatter_kernel<<<(P + 255) / 256, 256, smem_hist ? bytes : 0, stream>>>(cam, P, radii, g, b, im, smem_hist);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
 }
@@ -187,59 +221,79 @@ __device__ __forceinline__ void slab_entry(uint32_t id, const float* __restrict_
     C = make_float4(r, gg, bb, __uint_as_float(id));
 }
 
-// one CTA per tile: bitonic sort of the tile's bucket in shared memory on (depth bits << 32 | id), then the sorted
-// point list, keys and parameter slabs are written (coalesced) -- the sort and the gather never round-trip to HBM.
-__global__ void __launch_bounds__(256) tile_sort_gather_kernel(const float* __restrict__ colors, GeomState g,
-                                                               BinningState b, ImageState im) {
-    extern __shared__ __align__(16) unsigned long long skeys[];
-    const int tile = blockIdx.x;
-    const uint2 range = im.ranges[tile];
-    const int n = (int)(range.y - range.x);
-    if (n == 0) return;
-    int np = 32;
-    while (np < n) np <<= 1;
-    const unsigned long long* __restrict__ src = reinterpret_cast<const unsigned long long*>(b.bucket) + range.x;
-    for (int i = threadIdx.x; i < np; i += blockDim.x) skeys[i] = i < n ? src[i] : ~0ull;
-    __syncthreads();
-    for (int k = 2; k <= np; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int c = threadIdx.x; c < (np >> 1); c += blockDim.x) {
-                const int a = ((c & ~(j - 1)) << 1) | (c & (j - 1));
-                const int d = a | j;
-                const unsigned long long ka = skeys[a], kd = skeys[d];
-                const bool up = (a & k) == 0;
-                if ((ka > kd) == up) { skeys[a] = kd; skeys[d] = ka; }
+// one CTA per tile: radix sort of the tile's bucket inside the CTA (cub::BlockRadixSort, keys in registers) on
+// (depth bits << 32 | id), then the sorted point list, keys and parameter slabs are written coalesced -- the sort
+// and the gather never round-trip to HBM.  The CTA picks the smallest items-per-thread variant that fits.
+template <int ITEMS>
+struct TileSort {
+    using BRS = cub::BlockRadixSort<unsigned long long, 256, ITEMS>;
+    __device__ static void run(typename BRS::TempStorage& temp, const unsigned long long* __restrict__ src, int n,
+                               int id_bits, uint32_t tile, size_t out0, const float* __restrict__ colors,
+                               const GeomState& g, const BinningState& b) {
+        unsigned long long keys[ITEMS];
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {       // any input arrangement is fine: the keys are unique
+            const int i = k * 256 + (int)threadIdx.x;
+            keys[k] = i < n ? src[i] : ~0ull;
+        }
+        BRS(temp).Sort(keys, 0, id_bits);                    // LSD: low digits (Gaussian id) first ...
+        __syncthreads();
+        BRS(temp).SortBlockedToStriped(keys, 32, 64);        // ... then the 32 depth bits; striped = coalesced output
+        const unsigned long long tile_hi = (unsigned long long)tile << 32;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const int r = k * 256 + (int)threadIdx.x;
+            if (r < n) {
+                const uint32_t id = (uint32_t)keys[k];
+                const size_t o = out0 + r;
+                b.keys[o] = tile_hi | (keys[k] >> 32);
+                b.vals[o] = id;
+                float4 A, B, C;
+                slab_entry(id, colors, g, A, B, C);
+                b.slabA[o] = A;
+                b.slabB[o] = B;
+                b.slabC[o] = C;
             }
-            __syncthreads();
         }
     }
-    const unsigned long long tile_hi = (unsigned long long)(uint32_t)tile << 32;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const unsigned long long key = skeys[i];
-        const uint32_t id = (uint32_t)key;
-        const size_t o = (size_t)range.x + i;
-        b.keys[o] = tile_hi | (key >> 32);
-        b.vals[o] = id;
-        float4 A, B, C;
-        slab_entry(id, colors, g, A, B, C);
-        b.slabA[o] = A;
-        b.slabB[o] = B;
-        b.slabC[o] = C;
+};
+
+// BIG = false: tiles with n <= 2048 (2/4/8 keys per thread);  BIG = true: only tiles with 2048 < n <= 4096.
+// Two kernels so that the common case is not held at the register / shared-memory footprint of the rare one.
+template <bool BIG>
+__global__ void __launch_bounds__(256) tile_sort_gather_kernel(const float* __restrict__ colors, GeomState g,
+                                                               BinningState b, ImageState im, int id_bits) {
+    const uint32_t tile = blockIdx.x;
+    const uint2 range = im.ranges[tile];
+    const int n = (int)(range.y - range.x);
+    const unsigned long long* __restrict__ src = reinterpret_cast<const unsigned long long*>(b.bucket) + range.x;
+    if constexpr (BIG) {
+        __shared__ typename TileSort<16>::BRS::TempStorage t16;
+        if (n <= 2048) return;
+        TileSort<16>::run(t16, src, n, id_bits, tile, range.x, colors, g, b);
+    } else {
+        __shared__ union {
+            typename TileSort<2>::BRS::TempStorage t2;
+            typename TileSort<4>::BRS::TempStorage t4;
+            typename TileSort<8>::BRS::TempStorage t8;
+        } temp;
+        if (n == 0 || n > 2048) return;
+        if (n <= 512) TileSort<2>::run(temp.t2, src, n, id_bits, tile, range.x, colors, g, b);
+        else if (n <= 1024) TileSort<4>::run(temp.t4, src, n, id_bits, tile, range.x, colors, g, b);
+        else TileSort<8>::run(temp.t8, src, n, id_bits, tile, range.x, colors, g, b);
     }
 }
 
-int launch_tile_sort_gather(const Camera& cam, uint32_t max_count, const float* colors, GeomState g, BinningState b,
-                            ImageState im, cudaStream_t stream) {
-    uint32_t np = 32;
-    while (np < max_count) np <<= 1;
-    const size_t smem = (size_t)np * sizeof(unsigned long long);
-    static bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) {
-        GPSG_CUDA(cudaFuncSetAttribute(tile_sort_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_set = true;
-    }
-    tile_sort_gather_kernel<<<cam.grid_x * cam.grid_y, 256, smem, stream>>>(colors, g, b, im);
+int launch_tile_sort_gather(const Camera& cam, int P, uint32_t max_count, const float* colors, GeomState g,
+                            BinningState b, ImageState im, cudaStream_t stream) {
+    int id_bits = 1;
+    while (id_bits < 32 && (1ll << id_bits) < (long long)P) ++id_bits;
+    tile_sort_gather_kernel<false><<<cam.grid_x * cam.grid_y, 256, 0, stream>>>(colors, g, b, im, id_bits);
     GPSG_LAUNCH_CHECK();
+    if (max_count > 2048) {
+        tile_sort_gather_kernel<true><<<cam.grid_x * cam.grid_y, 256, 0, stream>>>(colors, g, b, im, id_bits);
+        GPSG_LAUNCH_CHECK();
+    }
     return GPSG_OK;
 }
 

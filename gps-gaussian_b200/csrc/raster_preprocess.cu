@@ -38,12 +38,19 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
                                                          const float* __restrict__ opacities,
                                                          const float* __restrict__ cov3D_precomp,
                                                          int32_t* __restrict__ radii, GeomState g,
-                                                         uint32_t* __restrict__ tile_count) {
+                                                         uint32_t* __restrict__ tile_count, int smem_hist) {
+    // Pairs-per-tile histogram, privatised per CTA in shared memory: the 256 consecutive (pixel-aligned) Gaussians
+    // of a CTA land in a handful of tiles, so ~1.3 M hot global atomics become a few dozen per CTA.
+    extern __shared__ uint32_t sh_cnt[];
+    const int tiles = cam.grid_x * cam.grid_y;
+    if (smem_hist) {
+        for (int t = threadIdx.x; t < tiles; t += blockDim.x) sh_cnt[t] = 0u;
+        __syncthreads();
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
     int32_t out_radius = 0;
     uint32_t out_tiles = 0;
-    do {
+    if (i < P) do {
         const float x = means3D[3 * i], y = means3D[3 * i + 1], z = means3D[3 * i + 2];
         const float* view = cam.view;
         const float* proj = cam.proj;
@@ -112,18 +119,30 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
         out_tiles = (uint32_t)area;
         if (tile_count)  // tile-bucket binning: pairs per tile (sizes the buckets, replaces the per-Gaussian scan)
             for (int tile_y = ry0; tile_y < ry1; ++tile_y)
-                for (int tile_x = rx0; tile_x < rx1; ++tile_x) atomicAdd(&tile_count[tile_y * cam.grid_x + tile_x], 1u);
+                for (int tile_x = rx0; tile_x < rx1; ++tile_x)
+                    atomicAdd(smem_hist ? &sh_cnt[tile_y * cam.grid_x + tile_x] : &tile_count[tile_y * cam.grid_x + tile_x], 1u);
     } while (0);
-    radii[i] = out_radius;
-    g.tiles_touched[i] = out_tiles;
+    if (i < P) {
+        radii[i] = out_radius;
+        g.tiles_touched[i] = out_tiles;
+    }
+    if (smem_hist) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+            const uint32_t c = sh_cnt[t];
+            if (c) atomicAdd(&tile_count[t], c);
+        }
+    }
 }
 
 int launch_preprocess(const Camera& cam, int P, const float* means3D, const float* scales, const float* rots,
                       const float* opacities, const float* cov3D_precomp, int32_t* radii, GeomState g,
                       uint32_t* tile_count, cudaStream_t stream) {
     if (P <= 0) return GPSG_OK;
-    preprocess_kernel<<<(P + 255) / 256, 256, 0, stream>>>(cam, P, means3D, scales, rots, opacities, cov3D_precomp,
-                                                          radii, g, tile_count);
+    const size_t hist_bytes = sizeof(uint32_t) * (size_t)cam.grid_x * cam.grid_y;
+    const int smem_hist = (tile_count && hist_bytes <= 48 * 1024) ? 1 : 0;   // larger images: direct global atomics
+    preprocess_kernel<<<(P + 255) / 256, 256, smem_hist ? hist_bytes : 0, stream>>>(
+        cam, P, means3D, scales, rots, opacities, cov3D_precomp, radii, g, tile_count, smem_hist);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
 }

@@ -75,6 +75,8 @@ def test_c1_forward_parity():
     (250, 4000, 0.6, 4.0, (0.3, 0.6, 0.9)),      # image not a multiple of 16, coloured bg, fat splats
     (64, 300, 0.3, 12.0, (1.0, 1.0, 1.0)),       # splats covering many tiles; saturating pixels (T<1e-4 stop)
     (130, 2000, 3.0, 1.0, (0.0, 0.0, 0.0)),      # wide cloud: many off-screen / frustum-clamped Gaussians
+    (64, 4500, 0.35, 1.5, (0.0, 0.0, 0.0)),      # 2-3.4k pairs per tile: the 16-keys-per-thread in-CTA sort variant
+    (48, 30000, 0.25, 1.0, (0.0, 0.0, 0.0)),     # > 4096 pairs in a tile: automatic fallback to the global radix path
 ])
 def test_forward_parity_edge_shapes(res, P, spread, mul, bg):
     sc = synth.random_cube_scene(P, res, spread=spread, scale_mul=mul, bg=bg, seed=11)
