@@ -1,0 +1,73 @@
+"""Multi-GPU host logic for the path: independent stereo view-pairs are the sharding unit.
+
+One process per GPU (`torch.distributed`, NCCL on GPUs / gloo in the CPU tests).  Inference needs NO data-path
+collective: each rank renders its own view-pairs; the only communication is a barrier and a MAX-reduce of the
+elapsed time (so throughput = all units / slowest rank), plus an optional gather of small per-rank results."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def world():
+    """(rank, world_size, local_rank) from the torchrun environment (1-process default)."""
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init(backend=None, device=None):
+    rank, ws, _ = world()
+    if ws > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
+        dist.init_process_group(backend, rank=rank, world_size=ws, **kw)
+    return rank, ws
+
+
+def shard_units(n_units, rank, world_size):
+    """Contiguous block partition of unit ids 0..n_units-1; sizes differ by at most one; every unit exactly once."""
+    base, rem = divmod(n_units, world_size)
+    start = rank * base + min(rank, rem)
+    return list(range(start, start + base + (1 if rank < rem else 0)))
+
+
+def unit_seeds(first_seed, units_per_rank, rank):
+    """Weak scaling (bench.py): rank r renders units with seeds first_seed + r*units_per_rank + k (reference seed 1314)."""
+    return [first_seed + rank * units_per_rank + k for k in range(units_per_rank)]
+
+
+def barrier(device=None):
+    if dist.is_initialized():
+        dist.barrier()
+    if device is not None and torch.cuda.is_available():
+        torch.cuda.synchronize(device)
+
+
+def max_over_ranks(value, device=None):
+    """MAX-reduce of a python float (the timed region's elapsed ms): throughput is set by the slowest rank."""
+    if not dist.is_initialized():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value, device=None):
+    if not dist.is_initialized():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def aggregate_throughput(units_this_rank, elapsed_ms, device=None):
+    """views/s of the whole job: (sum of units over ranks) / (max elapsed over ranks)."""
+    total = sum_over_ranks(units_this_rank, device)
+    ms = max_over_ranks(elapsed_ms, device)
+    return total / (ms * 1e-3), total, ms
+
+
+def finalize():
+    if dist.is_initialized():
+        dist.destroy_process_group()
