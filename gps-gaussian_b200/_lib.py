@@ -70,6 +70,14 @@ lib.gpsg_corr_sampler_forward.argtypes = [_i, _vp, _i, _i, _i, _i, _i, _vp, _i64
 lib.gpsg_corr_sampler_backward.restype = _i
 lib.gpsg_corr_sampler_backward.argtypes = [_i, _vp, _i, _i, _i, _i, _i, _vp, _i64, _vp, _i, _vp]
 
+lib.gpsg_corr_build_pyramid.restype = _i
+lib.gpsg_corr_build_pyramid.argtypes = [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, C.POINTER(C.c_void_p), _i]
+lib.gpsg_corr_lookup_pyramid_forward.restype = _i
+lib.gpsg_corr_lookup_pyramid_forward.argtypes = [_i, _vp, _i, _i, _i, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), _i,
+                                                 _vp, _i64, _i, _vp]
+lib.gpsg_corr_lookup_pyramid_backward.restype = _i
+lib.gpsg_corr_lookup_pyramid_backward.argtypes = [_i, _vp, _i, _i, _i, _i, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), _i,
+                                                  _vp, _i64, _i, _vp]
 lib.gpsg_profile_enable.restype = _i
 lib.gpsg_profile_enable.argtypes = [_i]
 lib.gpsg_profile_read.restype = _i
@@ -79,7 +87,8 @@ lib.gpsg_profile_stage_name.argtypes = [_i]
 
 EXPORTED = ["gpsg_last_error", "gpsg_version", "gpsg_rasterize_forward", "gpsg_rasterize_backward_workspace_bytes",
             "gpsg_rasterize_backward", "gpsg_mark_visible", "gpsg_geom_view", "gpsg_binning_view", "gpsg_image_view",
-            "gpsg_corr_sampler_forward", "gpsg_corr_sampler_backward", "gpsg_profile_enable", "gpsg_profile_read",
+            "gpsg_corr_sampler_forward", "gpsg_corr_sampler_backward", "gpsg_corr_build_pyramid",
+            "gpsg_corr_lookup_pyramid_forward", "gpsg_corr_lookup_pyramid_backward", "gpsg_profile_enable", "gpsg_profile_read",
             "gpsg_profile_stage_name"]
 
 

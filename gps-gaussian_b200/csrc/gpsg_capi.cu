@@ -149,7 +149,7 @@ struct Profiler {
 static thread_local Profiler g_prof;
 static const char* kStageNames[ST_COUNT] = {"preprocess", "scan", "duplicate", "sort", "gather_ranges", "tile_scan",
                                             "bucket_scatter", "tile_sort_gather", "render_forward",
-                                            "render_backward", "preprocess_backward", "corr_forward", "corr_backward"};
+                                            "render_backward", "preprocess_backward", "corr_forward", "corr_backward", "corr_build"};
 StageTimer::StageTimer(Stage s, cudaStream_t st, int launches) : stage(s), stream(st), slot(nullptr) {
     if (!g_prof.on) return;
     if (g_prof.next == g_prof.slots.size()) {
@@ -367,6 +367,43 @@ int gpsg_corr_sampler_backward(int device, void* stream_, int dtype, int B, int 
                            (cudaStream_t)stream_);
 }
 
+
+int gpsg_corr_build_pyramid(int device, void* stream_, int dtype, int B, int D, int H, int W1, int W2, const void* fmap1,
+                            const void* fmap2, void* const* vols, int levels) {
+    GPSG_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp32) or 1 (fp16)");
+    GPSG_REQUIRE(B >= 0 && D > 0 && H >= 0 && W1 >= 0 && W2 >= 0 && levels >= 1 && levels <= 4, "bad shape / levels");
+    if ((int64_t)B * H * W1 * W2 == 0) return GPSG_OK;
+    GPSG_REQUIRE(fmap1 && fmap2 && vols && vols[0], "NULL pointer");
+    for (int l = 1; l < levels; ++l) GPSG_REQUIRE(vols[l] != nullptr || (W2 >> l) == 0, "NULL pyramid level");
+    GPSG_CUDA(cudaSetDevice(device));
+    StageTimer t(ST_CORR_BUILD, (cudaStream_t)stream_, 1);
+    return launch_corr_build(dtype, B, D, H, W1, W2, fmap1, fmap2, vols[0], levels > 1 ? vols[1] : nullptr,
+                             levels > 2 ? vols[2] : nullptr, levels > 3 ? vols[3] : nullptr, levels, (cudaStream_t)stream_);
+}
+
+int gpsg_corr_lookup_pyramid_forward(int device, void* stream_, int dtype, int B, int H, int W1, const void* const* vols,
+                                     const int32_t* widths, int levels, const float* coords, int64_t coords_sb, int radius,
+                                     void* out) {
+    GPSG_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp32) or 1 (fp16)");
+    GPSG_REQUIRE(B >= 0 && H >= 0 && W1 >= 0 && levels >= 1 && levels <= 4 && radius >= 0 && radius <= 31, "bad shape");
+    if ((int64_t)B * H * W1 == 0) return GPSG_OK;
+    GPSG_REQUIRE(vols && widths && coords && out, "NULL pointer");
+    GPSG_CUDA(cudaSetDevice(device));
+    StageTimer t(ST_CORR_FWD, (cudaStream_t)stream_, 1);
+    return launch_corr_lookup_fwd(dtype, B, H, W1, vols, widths, levels, coords, coords_sb, radius, out, (cudaStream_t)stream_);
+}
+
+int gpsg_corr_lookup_pyramid_backward(int device, void* stream_, int dtype, int B, int H, int W1, void* const* grad_vols,
+                                      const int32_t* widths, int levels, const float* coords, int64_t coords_sb, int radius,
+                                      const void* grad_out) {
+    GPSG_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp32) or 1 (fp16)");
+    GPSG_REQUIRE(B >= 0 && H >= 0 && W1 >= 0 && levels >= 1 && levels <= 4 && radius >= 0 && radius <= 31, "bad shape");
+    if ((int64_t)B * H * W1 == 0) return GPSG_OK;
+    GPSG_REQUIRE(grad_vols && widths && coords && grad_out, "NULL pointer");
+    GPSG_CUDA(cudaSetDevice(device));
+    StageTimer t(ST_CORR_BWD, (cudaStream_t)stream_, 1);
+    return launch_corr_lookup_bwd(dtype, B, H, W1, grad_vols, widths, levels, coords, coords_sb, radius, grad_out, (cudaStream_t)stream_);
+}
 
 int gpsg_profile_enable(int on) {
     g_prof.on = on != 0;

@@ -120,11 +120,17 @@ int launch_corr_fwd(int dtype, int B, int H, int W1, int W2, const void* vol, in
                     const float* coords, int64_t csb, int r, void* out, cudaStream_t stream);
 int launch_corr_bwd(int dtype, int B, int H, int W1, int W2, const float* coords, int64_t csb, const void* gout, int r,
                     void* gvol, cudaStream_t stream);
+int launch_corr_build(int dtype, int B, int D, int H, int W1, int W2, const void* f1, const void* f2, void* v0, void* v1,
+                      void* v2, void* v3, int levels, cudaStream_t stream);
+int launch_corr_lookup_fwd(int dtype, int B, int H, int W1, const void* const* vols, const int* widths, int levels,
+                           const float* coords, int64_t csb, int r, void* out, cudaStream_t stream);
+int launch_corr_lookup_bwd(int dtype, int B, int H, int W1, void* const* gvols, const int* widths, int levels,
+                           const float* coords, int64_t csb, int r, const void* gout, cudaStream_t stream);
 
 
 // ---- optional per-stage timing (bench.py); see gpsg_profile_* in gpsg.h ---------------------
 enum Stage { ST_PREPROCESS = 0, ST_SCAN, ST_DUPLICATE, ST_SORT, ST_GATHER, ST_TILE_SCAN, ST_SCATTER, ST_TILE_SORT, ST_RENDER_FWD, ST_RENDER_BWD,
-             ST_PREPROCESS_BWD, ST_CORR_FWD, ST_CORR_BWD, ST_COUNT };
+             ST_PREPROCESS_BWD, ST_CORR_FWD, ST_CORR_BWD, ST_CORR_BUILD, ST_COUNT };
 struct StageTimer {  // RAII: records begin/end events on `stream` when profiling is on
     StageTimer(Stage s, cudaStream_t stream, int launches);
     ~StageTimer();

@@ -129,6 +129,20 @@ GPSG_API int gpsg_corr_sampler_backward(int device, void* stream, int dtype, int
                                const float* coords, int64_t coords_sb, const void* grad_out, int radius,
                                void* grad_volume);
 
+/* ---- fused forms of the correlation block (reference core/corr.py:31-61), used by the mirrored CorrBlockFast1D ----
+ * gpsg_corr_build_pyramid: fmap1[B,D,H,W1], fmap2[B,D,H,W2] (contiguous, dtype 0=fp32 1=fp16) ->
+ *   vol[l][B,H,W1,W2>>l], l < levels<=4 : einsum/sqrt(D) then avg_pool2d([1,2]) per level, each level rounded to dtype.
+ * gpsg_corr_lookup_pyramid_forward: all levels of CorrBlockFast1D.__call__ in one launch -> out[B, levels*(2r+1), H, W1]
+ *   (coords: channel 0 of [B,C,H,W1] fp32, level l uses coords / 2^l).  _backward: grad_out -> grad_vol[l] (fully written). */
+GPSG_API int gpsg_corr_build_pyramid(int device, void* stream, int dtype, int B, int D, int H, int W1, int W2,
+                                     const void* fmap1, const void* fmap2, void* const* vols, int levels);
+GPSG_API int gpsg_corr_lookup_pyramid_forward(int device, void* stream, int dtype, int B, int H, int W1,
+                                              const void* const* vols, const int32_t* widths, int levels,
+                                              const float* coords, int64_t coords_sb, int radius, void* out);
+GPSG_API int gpsg_corr_lookup_pyramid_backward(int device, void* stream, int dtype, int B, int H, int W1,
+                                               void* const* grad_vols, const int32_t* widths, int levels,
+                                               const float* coords, int64_t coords_sb, int radius, const void* grad_out);
+
 /* ---- measurement hooks (used by bench.py; off by default) -----------------------------------
  * When enabled, every stage of the forward/backward is bracketed by CUDA events on the launching stream.
  * gpsg_profile_read() synchronises, then returns for stage i: total_ms[i] (summed over the calls since the last

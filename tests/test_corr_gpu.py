@@ -97,3 +97,52 @@ def test_autograd_sampler_linear_and_adjoint():
     lhs = float((out.detach().double() * g.double()).sum())
     rhs = float((vol.detach().double() * vol.grad.double()).sum())
     assert abs(lhs - rhs) < 1e-3 * max(1.0, abs(lhs))
+
+
+def _unfused_block(f1, f2, coords, levels=4, r=4):
+    """The reference's op sequence (core/corr.py:31-61) with torch ops + the per-level sampler: einsum, /sqrt(D),
+    avg_pool2d, CorrSampler per level, cat."""
+    import torch.nn.functional as F
+    from gps_gaussian_b200.corr import CorrSampler
+    B, D, H, W1 = f1.shape
+    W2 = f2.shape[3]
+    corr = torch.einsum('aijk,aijh->ajkh', f1, f2).reshape(B, H, W1, 1, W2).contiguous() / torch.sqrt(torch.tensor(D).float())
+    corr = corr.reshape(B * H * W1, 1, 1, W2)
+    outs = []
+    for i in range(levels):
+        lvl = corr.view(B, H, W1, -1)
+        outs.append(CorrSampler.apply(lvl, coords[:, [0]] / 2 ** i, r))
+        corr = F.avg_pool2d(corr, [1, 2], stride=[1, 2])
+    return torch.cat(outs, 1)
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 3, 40), (1, 192, 5, 128), (2, 17, 2, 150)])
+def test_fused_block_matches_unfused_incl_fmap_grads(shape):
+    """Fused build+pyramid and fused 4-level lookup == the reference's op-by-op sequence (fp32), outputs and d/dfmap."""
+    from gps_gaussian_b200.corr import CorrBlockFast1D
+    B, D, H, W = shape
+    f1n, f2n, cn = synth.corr_inputs(B, D, H, W, seed=5)
+    g = torch.randn(B, 36, H, W, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    res = []
+    for fused in (True, False):
+        f1 = _cuda(f1n).requires_grad_(True); f2 = _cuda(f2n).requires_grad_(True)
+        out = CorrBlockFast1D(f1, f2, num_levels=4, radius=4)(_cuda(cn)) if fused else _unfused_block(f1, f2, _cuda(cn))
+        (out * g).sum().backward()
+        res.append((out.detach(), f1.grad, f2.grad))
+    for a, b in zip(*res):
+        assert a.shape == b.shape
+        assert float((a - b).abs().max()) < 2e-4 * max(1.0, float(b.abs().max()))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.float16, 3e-3)])
+def test_fused_pyramid_build_vs_oracle(dtype, tol):
+    from gps_gaussian_b200.corr import CorrBlockFast1D
+    f1n, f2n, _ = synth.corr_inputs(2, 192, 6, 128, seed=3)
+    f1, f2 = _cuda(f1n, dtype), _cuda(f2n, dtype)
+    blk = CorrBlockFast1D(f1, f2, num_levels=4, radius=4)
+    o = CorrOracle("f64")
+    pyr = o.pyramid(f1.float().cpu().numpy(), f2.float().cpu().numpy(), 4)       # oracle sees the quantised inputs
+    for i in range(4):
+        got = blk.corr_pyramid[i]
+        assert got.shape == (2, 6, 128, 1, 128 >> i) and got.dtype == dtype
+        assert np.abs(got.squeeze(3).float().cpu().numpy() - pyr[i]).max() < tol * max(1.0, np.abs(pyr[i]).max())
