@@ -70,6 +70,16 @@ lib.gpsg_corr_sampler_forward.argtypes = [_i, _vp, _i, _i, _i, _i, _i, _vp, _i64
 lib.gpsg_corr_sampler_backward.restype = _i
 lib.gpsg_corr_sampler_backward.argtypes = [_i, _vp, _i, _i, _i, _i, _i, _vp, _i64, _vp, _i, _vp]
 
+lib.gpsg_raster_geom_bytes.restype = _sz
+lib.gpsg_raster_geom_bytes.argtypes = [_i]
+lib.gpsg_raster_binning_bytes.restype = _sz
+lib.gpsg_raster_binning_bytes.argtypes = [_i64]
+lib.gpsg_raster_image_bytes.restype = _sz
+lib.gpsg_raster_image_bytes.argtypes = [_i, _i]
+lib.gpsg_raster_status_ptr.restype = _vp
+lib.gpsg_raster_status_ptr.argtypes = [_vp, _i, _i]
+lib.gpsg_rasterize_forward_planned.restype = _i
+lib.gpsg_rasterize_forward_planned.argtypes = [C.POINTER(RasterSettings), _i, _vp, _i] + [_vp] * 10 + [_i64, _vp, _vp]
 lib.gpsg_corr_build_pyramid.restype = _i
 lib.gpsg_corr_build_pyramid.argtypes = [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, C.POINTER(C.c_void_p), _i]
 lib.gpsg_corr_lookup_pyramid_forward.restype = _i
@@ -88,7 +98,9 @@ lib.gpsg_profile_stage_name.argtypes = [_i]
 EXPORTED = ["gpsg_last_error", "gpsg_version", "gpsg_rasterize_forward", "gpsg_rasterize_backward_workspace_bytes",
             "gpsg_rasterize_backward", "gpsg_mark_visible", "gpsg_geom_view", "gpsg_binning_view", "gpsg_image_view",
             "gpsg_corr_sampler_forward", "gpsg_corr_sampler_backward", "gpsg_corr_build_pyramid",
-            "gpsg_corr_lookup_pyramid_forward", "gpsg_corr_lookup_pyramid_backward", "gpsg_profile_enable", "gpsg_profile_read",
+            "gpsg_corr_lookup_pyramid_forward", "gpsg_corr_lookup_pyramid_backward", "gpsg_raster_geom_bytes",
+            "gpsg_raster_binning_bytes", "gpsg_raster_image_bytes", "gpsg_raster_status_ptr",
+            "gpsg_rasterize_forward_planned", "gpsg_profile_enable", "gpsg_profile_read",
             "gpsg_profile_stage_name"]
 
 

@@ -217,7 +217,7 @@ int gpsg_rasterize_forward(const GpsgRasterSettings* s, int device, void* stream
         { StageTimer t(ST_PREPROCESS, stream, 1); rc = launch_preprocess(cam, P, means3D, scales, rotations, opacities, cov3D_precomp, radii, g, im.tile_count, stream); }
         if (rc) return rc;
     }
-    { StageTimer t(ST_TILE_SCAN, stream, 1); rc = launch_tile_scan(cam, im, stream); }
+    { StageTimer t(ST_TILE_SCAN, stream, 1); rc = launch_tile_scan(cam, im, 0u, stream); }
     if (rc) return rc;
     if (P > 0) {
         uint32_t* slot = pinned_slot();
@@ -257,6 +257,49 @@ int gpsg_rasterize_forward(const GpsgRasterSettings* s, int device, void* stream
     if (rc) return rc;
     if (s->debug) GPSG_CUDA(cudaStreamSynchronize(stream));
     return GPSG_OK;
+}
+
+size_t gpsg_raster_geom_bytes(int P) { return GeomState::required(P > 0 ? P : 0, scan_temp_bytes(P > 0 ? P : 0)); }
+size_t gpsg_raster_binning_bytes(int64_t capacity_pairs) { return BinningState::required((size_t)(capacity_pairs > 0 ? capacity_pairs : 0), 0); }
+size_t gpsg_raster_image_bytes(int W, int H) { return ImageState::required(W, H); }
+const uint32_t* gpsg_raster_status_ptr(const void* image_buffer, int W, int H) {
+    if (!image_buffer || W <= 0 || H <= 0) return nullptr;
+    return ImageState::carve(const_cast<void*>(image_buffer), W, H).totals;
+}
+
+int gpsg_rasterize_forward_planned(const GpsgRasterSettings* s, int device, void* stream_, int P, const float* means3D,
+                                   const float* colors_precomp, const float* opacities, const float* scales,
+                                   const float* rotations, const float* cov3D_precomp, float* out_color, int32_t* radii,
+                                   void* geom_buffer, void* binning_buffer, int64_t capacity_pairs, void* image_buffer,
+                                   uint32_t* status_host) {
+    GPSG_REQUIRE(s != nullptr, "settings is NULL");
+    GPSG_REQUIRE(P > 0, "planned forward needs P > 0");
+    GPSG_REQUIRE(s->image_width > 0 && s->image_height > 0, "image size must be positive");
+    GPSG_REQUIRE(means3D && colors_precomp && opacities && out_color && radii, "a required pointer is NULL");
+    GPSG_REQUIRE(((scales != nullptr && rotations != nullptr) != (cov3D_precomp != nullptr)),
+                 "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+    GPSG_REQUIRE(geom_buffer && binning_buffer && image_buffer && capacity_pairs > 0 && capacity_pairs < (1ll << 31),
+                 "planned forward: buffers / capacity missing");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GPSG_CUDA(cudaSetDevice(device));
+    const Camera cam = make_camera(*s);
+    GeomState g = GeomState::carve(geom_buffer, P, 0);
+    ImageState im = ImageState::carve(image_buffer, cam.W, cam.H);
+    BinningState b = BinningState::carve(binning_buffer, (size_t)capacity_pairs, 0);
+    const int tiles = cam.grid_x * cam.grid_y;
+    int rc = GPSG_OK;
+    GPSG_CUDA(cudaMemsetAsync(im.tile_count, 0, sizeof(uint32_t) * (size_t)tiles, stream));
+    { StageTimer t(ST_PREPROCESS, stream, 1); rc = launch_preprocess(cam, P, means3D, scales, rotations, opacities, cov3D_precomp, radii, g, im.tile_count, stream); }
+    if (rc) return rc;
+    { StageTimer t(ST_TILE_SCAN, stream, 1); rc = launch_tile_scan(cam, im, (uint32_t)capacity_pairs, stream); }
+    if (rc) return rc;
+    if (status_host) GPSG_CUDA(cudaMemcpyAsync(status_host, im.totals, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    { StageTimer t(ST_SCATTER, stream, 1); rc = launch_bucket_scatter(cam, P, radii, g, b, im, stream); }
+    if (rc) return rc;
+    { StageTimer t(ST_TILE_SORT, stream, 2); rc = launch_tile_sort_gather(cam, P, kMaxTileSort, colors_precomp, g, b, im, stream); }
+    if (rc) return rc;
+    { StageTimer t(ST_RENDER_FWD, stream, 1); rc = launch_render_forward(cam, b, im, out_color, stream); }
+    return rc;
 }
 
 size_t gpsg_rasterize_backward_workspace_bytes(int P) { return align_up(sizeof(float4) * (size_t)(P > 0 ? P : 1)) + 256; }

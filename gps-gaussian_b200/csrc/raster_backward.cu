@@ -35,7 +35,7 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32) render_backward_kernel(c
                                                                              const float4* __restrict__ slabA,
                                                                              const float4* __restrict__ slabB,
                                                                              const float4* __restrict__ slabC,
-                                                                             const uint2* __restrict__ ranges,
+                                                                             const uint2* __restrict__ ranges, const uint32_t* __restrict__ status,
                                                                              const float* __restrict__ final_T,
                                                                              const uint32_t* __restrict__ n_contrib,
                                                                              const float* __restrict__ dL_dpix,
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32) render_backward_kernel(c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_y = blockIdx.y >> 1, half = blockIdx.y & 1;
     const int tile = tile_y * cam.grid_x + blockIdx.x;
-    const uint2 range = ranges[tile];
+    const uint2 range = status[2] ? make_uint2(0u, 0u) : ranges[tile];   // planned-mode overflow: render nothing
     const int total = (int)(range.y - range.x);
 
     // per-pixel state (consumer warps only; the producer warp's lanes map outside and stay inert)
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32) render_backward_kernel(c
 int launch_render_backward(const Camera& cam, BinningState b, ImageState im, const float* dL_dpix, float* dL_dmeans2D,
                            float4* dL_dconic_op, float* dL_dcolors, cudaStream_t stream) {
     dim3 grid(cam.grid_x, cam.grid_y * 2);
-    render_backward_kernel<<<grid, (kBwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges,
+    render_backward_kernel<<<grid, (kBwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges, im.totals,
                                                                      im.final_T, im.n_contrib, dL_dpix, dL_dmeans2D,
                                                                      dL_dconic_op, dL_dcolors);
     GPSG_LAUNCH_CHECK();

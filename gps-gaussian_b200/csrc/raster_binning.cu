@@ -81,7 +81,7 @@ int run_sort(BinningState b, size_t N, int end_bit, cudaStream_t stream) {
 // =====================================================================================================
 
 // one CTA: exclusive scan of the per-tile counts -> ranges[t] = (start, end); totals = (N, max count); cursors = 0
-__global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, ImageState im) {
+__global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, ImageState im, uint32_t capacity) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t carry, smax;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -122,11 +122,16 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, ImageState i
     local_max = __reduce_max_sync(0xffffffffu, local_max);
     if (lane == 0) atomicMax(&smax, local_max);
     __syncthreads();
-    if (tid == 0) { im.totals[0] = carry; im.totals[1] = smax; }
+    if (tid == 0) {
+        im.totals[0] = carry;
+        im.totals[1] = smax;
+        // planned (sync-free) mode: later kernels skip their work if the pairs do not fit / a tile is too long
+        im.totals[2] = (capacity != 0u && (carry > capacity || smax > kMaxTileSort)) ? 1u : 0u;
+    }
 }
 
-int launch_tile_scan(const Camera& cam, ImageState im, cudaStream_t stream) {
-    tile_scan_kernel<<<1, 1024, 0, stream>>>(cam.grid_x * cam.grid_y, im);
+int launch_tile_scan(const Camera& cam, ImageState im, uint32_t capacity, cudaStream_t stream) {
+    tile_scan_kernel<<<1, 1024, 0, stream>>>(cam.grid_x * cam.grid_y, im, capacity);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
 }
@@ -138,6 +143,7 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(const __grid_consta
                                                              const int32_t* __restrict__ radii, GeomState g,
                                                              BinningState b, ImageState im, int smem_hist) {
     extern __shared__ uint32_t sh[];            // [tiles] local counts, then [tiles] CTA bases
+    if (im.totals[2]) return;                   // planned mode overflow: nothing may be written
     const int tiles = cam.grid_x * cam.grid_y;
     uint32_t* sh_cnt = sh;
     uint32_t* sh_base = sh + tiles;
@@ -263,6 +269,7 @@ struct TileSort {
 template <bool BIG>
 __global__ void __launch_bounds__(256) tile_sort_gather_kernel(const float* __restrict__ colors, GeomState g,
                                                                BinningState b, ImageState im, int id_bits) {
+    if (im.totals[2]) return;                   // planned mode overflow
     const uint32_t tile = blockIdx.x;
     const uint2 range = im.ranges[tile];
     const int n = (int)(range.y - range.x);

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__((kFwdWarps + 1) * 32) render_forward_kernel(co
                                                                             const float4* __restrict__ slabA,
                                                                             const float4* __restrict__ slabB,
                                                                             const float4* __restrict__ slabC,
-                                                                            const uint2* __restrict__ ranges,
+                                                                            const uint2* __restrict__ ranges, const uint32_t* __restrict__ status,
                                                                             float* __restrict__ final_T,
                                                                             uint32_t* __restrict__ n_contrib,
                                                                             float* __restrict__ out_color) {
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__((kFwdWarps + 1) * 32) render_forward_kernel(co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile_y = blockIdx.y >> 1, half = blockIdx.y & 1;   // two CTAs per 16x16 tile
     const int tile = tile_y * cam.grid_x + blockIdx.x;
-    const uint2 range = ranges[tile];
+    const uint2 range = status[2] ? make_uint2(0u, 0u) : ranges[tile];   // planned-mode overflow: render nothing
     const int total = (int)(range.y - range.x);
     const int nbatch = (total + kFwdChunk - 1) / kFwdChunk;
 
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__((kFwdWarps + 1) * 32) render_forward_kernel(co
 
 int launch_render_forward(const Camera& cam, BinningState b, ImageState im, float* out_color, cudaStream_t stream) {
     dim3 grid(cam.grid_x, cam.grid_y * 2);
-    render_forward_kernel<<<grid, (kFwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges,
+    render_forward_kernel<<<grid, (kFwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges, im.totals,
                                                                     im.final_T, im.n_contrib, out_color);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;

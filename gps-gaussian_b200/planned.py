@@ -1,0 +1,85 @@
+"""Sync-free rasterizer front end over `gpsg_rasterize_forward_planned` (include/gpsg.h).
+
+`PlannedRasterizer` owns persistent scratch buffers sized for a pair capacity, so a forward is a fixed sequence of
+kernel launches with no host synchronisation and no allocation: the CPU runs ahead of the GPU, and the whole
+forward can be captured into a CUDA graph (`capture()` / `replay()`).  The price is a deferred check: after the
+caller next synchronises, `ok()` tells whether the pairs fitted; if not, `grow()` and render again (or use the
+exact, one-sync entry point behind `diff_gaussian_rasterization.GaussianRasterizer`).
+
+This is the serving path (fixed scene size class, many views): reference test_view_interp.py:39-47 renders
+`novel_view_nums` views of one pair in a loop -- with this class that loop contains no sync at all.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .introspect import make_settings
+
+
+class PlannedRasterizer:
+    def __init__(self, P, height, width, capacity_pairs, device="cuda"):
+        self.dev = torch.device(device)
+        self.idx = self.dev.index if self.dev.index is not None else torch.cuda.current_device()
+        self.P, self.H, self.W = int(P), int(height), int(width)
+        new = lambda n: torch.empty(int(n), dtype=torch.uint8, device=self.dev)
+        self.geom = new(_lib.lib.gpsg_raster_geom_bytes(self.P))
+        self.image = new(_lib.lib.gpsg_raster_image_bytes(self.W, self.H))
+        self.color = torch.empty((3, self.H, self.W), dtype=torch.float32, device=self.dev)
+        self.radii = torch.empty((self.P,), dtype=torch.int32, device=self.dev)
+        self.status_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self._alloc_binning(int(capacity_pairs))
+        self.graph = None
+
+    def _alloc_binning(self, cap):
+        self.capacity = int(cap)
+        self.binning = torch.empty(int(_lib.lib.gpsg_raster_binning_bytes(self.capacity)), dtype=torch.uint8, device=self.dev)
+
+    def forward(self, settings, means3D, colors, opacity, scales, rots, cov3D_precomp=None):
+        """Enqueue one forward on the current stream.  Inputs: contiguous fp32 CUDA tensors; `settings`: a
+        `_lib.RasterSettings` (see introspect.make_settings) or a synth scene dict.  Returns self.color (valid once the
+        stream has run AND ok() holds)."""
+        if isinstance(settings, dict):
+            settings = make_settings(settings)
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        rc = _lib.lib.gpsg_rasterize_forward_planned(
+            C.byref(settings), self.idx, C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream), self.P, p(means3D),
+            p(colors), p(opacity), p(scales), p(rots), p(cov3D_precomp), p(self.color), p(self.radii), p(self.geom),
+            p(self.binning), self.capacity, p(self.image), C.c_void_p(self.status_host.data_ptr()))
+        _lib.check(rc, "gpsg_rasterize_forward_planned")
+        return self.color
+
+    # ---- deferred status (call after a synchronisation that covers the forward) ----
+    def status(self):
+        n, mx, ov, _ = (int(v) for v in self.status_host.tolist())
+        return dict(num_rendered=n, max_tile=mx, overflow=bool(ov))
+
+    def ok(self):
+        return not self.status()["overflow"]
+
+    def grow(self, factor=1.5):
+        st = self.status()
+        self._alloc_binning(max(int(st["num_rendered"] * factor), int(self.capacity * factor)))
+        self.graph = None
+
+    # ---- CUDA graph ----
+    def capture(self, settings, means3D, colors, opacity, scales, rots, cov3D_precomp=None):
+        """Capture one forward (fixed input pointers / camera) into a CUDA graph; replay() re-runs it."""
+        if isinstance(settings, dict):
+            settings = make_settings(settings)
+        self._keep = (settings, means3D, colors, opacity, scales, rots, cov3D_precomp)
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            self.forward(*self._keep)                      # warm-up outside capture (lazy module loads etc.)
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward(*self._keep)
+        self.graph = g
+        return g
+
+    def replay(self):
+        self.graph.replay()
+        return self.color

@@ -20,6 +20,8 @@ def init(backend=None, device=None):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        # NCCL prints its version banner to STDOUT at INFO/VERSION level; bench.py's stdout must be one JSON line
+        os.environ["NCCL_DEBUG"] = os.environ.get("GPSG_NCCL_DEBUG", "WARN")
         kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
         dist.init_process_group(backend, rank=rank, world_size=ws, **kw)
     return rank, ws

@@ -76,6 +76,24 @@ GPSG_API int gpsg_rasterize_forward(const GpsgRasterSettings* settings, int devi
                            void* binning_user, gpsg_alloc_fn image_alloc, void* image_user,
                            int32_t* num_rendered);
 
+/* ---- sync-free ("planned") forward: same computation as gpsg_rasterize_forward, but every buffer is provided by the
+ * caller up front and there is NO host synchronisation, so the call is CUDA-graph capturable and the CPU can run
+ * ahead.  `capacity_pairs` bounds the number of (tile,Gaussian) pairs the binning buffer can hold.  The kernels
+ * read the actual pair count from device memory; if it exceeds the capacity (or a tile list exceeds the in-CTA sort
+ * limit) they set the overflow word and skip their work: the caller must inspect status[2] once it next
+ * synchronises and, if set, retry with a larger capacity / the exact entry point (out_color is then undefined).
+ * status (device pointer into image_buf, see gpsg_raster_status_ptr; optionally mirrored to `status_host`, pinned):
+ * [0] pairs N, [1] longest tile list, [2] overflow flag.  For gpsg_rasterize_backward pass num_rendered = capacity. */
+GPSG_API size_t gpsg_raster_geom_bytes(int P);
+GPSG_API size_t gpsg_raster_binning_bytes(int64_t capacity_pairs);
+GPSG_API size_t gpsg_raster_image_bytes(int W, int H);
+GPSG_API const uint32_t* gpsg_raster_status_ptr(const void* image_buffer, int W, int H);
+GPSG_API int gpsg_rasterize_forward_planned(const GpsgRasterSettings* settings, int device, void* stream, int P,
+                                            const float* means3D, const float* colors_precomp, const float* opacities,
+                                            const float* scales, const float* rotations, const float* cov3D_precomp,
+                                            float* out_color, int32_t* radii, void* geom_buffer, void* binning_buffer,
+                                            int64_t capacity_pairs, void* image_buffer, uint32_t* status_host);
+
 /* ---- replaces _C.rasterize_gaussians_backward (Appendix A.6-A.8) ----------------------------
  * geom/binning/image buffers are the ones the forward allocated.  All dL_* outputs are written
  * (zero for culled Gaussians); dL_dmeans2D is [P,3] (z unused), dL_dcov3D [P,6] and dL_dsh

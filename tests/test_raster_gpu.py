@@ -251,3 +251,35 @@ def test_radix_fallback_path_is_bit_identical_to_tile_bucket_path():
                         "-k", "c1_forward_parity or edge_shapes or c1_backward_parity or idempotent"],
                        env=env, cwd=root, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_planned_sync_free_forward_and_cuda_graph():
+    """gpsg_rasterize_forward_planned: no host sync, caller buffers, device-side overflow flag, graph capture;
+    bit-identical image / radii to the exact entry point."""
+    from gps_gaussian_b200.introspect import to_device
+    from gps_gaussian_b200.planned import PlannedRasterizer
+    sc = synth.random_cube_scene(10_000, 256, seed=8, bg=(0.05, 0.1, 0.2))
+    ref = _run(sc)
+    d = to_device(sc)
+    args = (sc, d["means3D"], d["colors"], d["opacity"], d["scales"], d["rots"])
+    pr = PlannedRasterizer(10_000, 256, 256, capacity_pairs=int(ref.num_rendered * 1.25))
+    out = pr.forward(*args)
+    torch.cuda.synchronize()
+    st = pr.status()
+    assert not st["overflow"] and st["num_rendered"] == ref.num_rendered
+    assert torch.equal(out, ref.color) and torch.equal(pr.radii, ref.radii)
+    # overflow: capacity too small -> flagged, nothing written out of bounds, recoverable with grow()
+    small = PlannedRasterizer(10_000, 256, 256, capacity_pairs=ref.num_rendered // 2)
+    small.forward(*args)
+    torch.cuda.synchronize()
+    assert small.status()["overflow"] and not small.ok()
+    small.grow()
+    out2 = small.forward(*args)
+    torch.cuda.synchronize()
+    assert small.ok() and torch.equal(out2, ref.color)
+    # CUDA graph capture + replay
+    pr.capture(*args)
+    pr.color.zero_()
+    pr.replay(); pr.replay()
+    torch.cuda.synchronize()
+    assert pr.ok() and torch.equal(pr.color, ref.color)
