@@ -233,18 +233,91 @@ __device__ __forceinline__ void slab_entry(uint32_t id, const float* __restrict_
 template <int ITEMS>
 struct TileSort {
     using BRS = cub::BlockRadixSort<unsigned long long, 256, ITEMS>;
-    __device__ static void run(typename BRS::TempStorage& temp, const unsigned long long* __restrict__ src, int n,
-                               int id_bits, uint32_t tile, size_t out0, const float* __restrict__ colors,
-                               const GeomState& g, const BinningState& b) {
+    union Smem {
+        typename BRS::TempStorage sort;
+        unsigned long long keys[256 * ITEMS];   // sorted keys, for the equal-depth fix-up
+    };
+
+    // Sorts the tile's (depth bits << 32 | id) keys and writes point list, keys and slabs.
+    //  * only the depth bits that differ inside the tile are radix-sorted (block-wide min/max of the keys);
+    //  * the Gaussian id (low word) is NOT radix-sorted: equal-depth runs -- the only place it matters -- are found
+    //    after the sort and ordered by id in shared memory.  A run longer than kMaxRun falls back to the full
+    //    (id + depth) radix sort, so degenerate inputs (thousands of identical depths) stay correct and bounded.
+    static constexpr int kMaxRun = 16;
+    __device__ static void run(Smem& sm, int* flags, const unsigned long long* __restrict__ src, int n, int id_bits,
+                               uint32_t tile, size_t out0, const float* __restrict__ colors, const GeomState& g,
+                               const BinningState& b) {
         unsigned long long keys[ITEMS];
+        unsigned long long kmin = ~0ull, kmax = 0ull;
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {       // any input arrangement is fine: the keys are unique
             const int i = k * 256 + (int)threadIdx.x;
             keys[k] = i < n ? src[i] : ~0ull;
+            if (i < n) { kmin = min(kmin, keys[k]); kmax = max(kmax, keys[k]); }
         }
-        BRS(temp).Sort(keys, 0, id_bits);                    // LSD: low digits (Gaussian id) first ...
+        // block-wide min / max of the depth words -> highest differing depth bit
+        uint32_t dmin = (uint32_t)(kmin >> 32), dmax = (uint32_t)(kmax >> 32);
+        dmin = __reduce_min_sync(0xffffffffu, dmin);
+        dmax = __reduce_max_sync(0xffffffffu, dmax);
+        if (threadIdx.x == 0) { flags[0] = 0x7fffffff; flags[1] = 0; flags[2] = 0; }
         __syncthreads();
-        BRS(temp).SortBlockedToStriped(keys, 32, 64);        // ... then the 32 depth bits; striped = coalesced output
+        if ((threadIdx.x & 31) == 0) { atomicMin(&flags[0], (int)(dmin >> 1)); atomicMax(&flags[1], (int)(dmax >> 1)); }
+        __syncthreads();
+        // Keys are re-based on the tile's smallest depth word so that only bit_length(max - min) depth bits need
+        // sorting; padding keys get the next higher bit, i.e. they are strictly greater than every real key inside
+        // the sorted window (with un-rebased keys a real key with an all-ones window would tie with the padding).
+        const uint32_t dlo = (uint32_t)flags[0] << 1;                              // <= true min (low bit dropped)
+        const uint32_t span = (((uint32_t)flags[1] << 1) | 1u) - dlo;              // >= true max - dlo
+        const int w = 32 - __clz(span);                                            // 1..32 (depth < 2^31 => w <= 31)
+        const unsigned long long base = (unsigned long long)dlo << 32;
+        const unsigned long long pad = 1ull << (32 + w);
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) keys[k] = (k * 256 + (int)threadIdx.x) < n ? keys[k] - base : pad;
+        BRS(sm.sort).SortBlockedToStriped(keys, 32, 32 + w + 1);
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) keys[k] += base;                            // (padding ranks >= n are never read)
+        __syncthreads();
+        // ---- equal-depth runs: order by id ----
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) sm.keys[k * 256 + (int)threadIdx.x] = keys[k];   // rank r = k*256 + tid
+        __syncthreads();
+        bool redo = false;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const int r = k * 256 + (int)threadIdx.x;
+            if (r + 1 < n) {
+                const uint32_t d = (uint32_t)(sm.keys[r] >> 32);
+                const bool start = (r == 0 || (uint32_t)(sm.keys[r - 1] >> 32) != d) && (uint32_t)(sm.keys[r + 1] >> 32) == d;
+                if (start) {
+                    int e = r + 1;
+                    while (e + 1 < n && (uint32_t)(sm.keys[e + 1] >> 32) == d) ++e;       // run = [r, e]
+                    if (e - r + 1 > kMaxRun) redo = true;
+                    else
+                        for (int a = r + 1; a <= e; ++a) {                                // insertion sort (short run)
+                            const unsigned long long v = sm.keys[a];
+                            int c = a - 1;
+                            while (c >= r && sm.keys[c] > v) { sm.keys[c + 1] = sm.keys[c]; --c; }
+                            sm.keys[c + 1] = v;
+                        }
+                }
+            }
+        }
+        if (redo) flags[2] = 1;
+        __syncthreads();
+        if (flags[2]) {   // degenerate tile: full LSD radix sort, id digits first, then all depth digits
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                const int i = k * 256 + (int)threadIdx.x;
+                keys[k] = i < n ? src[i] : ~0ull;
+            }
+            __syncthreads();
+            BRS(sm.sort).Sort(keys, 0, id_bits);
+            __syncthreads();
+            BRS(sm.sort).SortBlockedToStriped(keys, 32, 64);
+        } else {
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) keys[k] = sm.keys[k * 256 + (int)threadIdx.x];
+        }
         const unsigned long long tile_hi = (unsigned long long)tile << 32;
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
@@ -269,25 +342,26 @@ struct TileSort {
 template <bool BIG>
 __global__ void __launch_bounds__(256) tile_sort_gather_kernel(const float* __restrict__ colors, GeomState g,
                                                                BinningState b, ImageState im, int id_bits) {
+    __shared__ int flags[4];
     if (im.totals[2]) return;                   // planned mode overflow
     const uint32_t tile = blockIdx.x;
     const uint2 range = im.ranges[tile];
     const int n = (int)(range.y - range.x);
     const unsigned long long* __restrict__ src = reinterpret_cast<const unsigned long long*>(b.bucket) + range.x;
     if constexpr (BIG) {
-        __shared__ typename TileSort<16>::BRS::TempStorage t16;
+        __shared__ typename TileSort<16>::Smem t16;
         if (n <= 2048) return;
-        TileSort<16>::run(t16, src, n, id_bits, tile, range.x, colors, g, b);
+        TileSort<16>::run(t16, flags, src, n, id_bits, tile, range.x, colors, g, b);
     } else {
         __shared__ union {
-            typename TileSort<2>::BRS::TempStorage t2;
-            typename TileSort<4>::BRS::TempStorage t4;
-            typename TileSort<8>::BRS::TempStorage t8;
+            typename TileSort<2>::Smem t2;
+            typename TileSort<4>::Smem t4;
+            typename TileSort<8>::Smem t8;
         } temp;
         if (n == 0 || n > 2048) return;
-        if (n <= 512) TileSort<2>::run(temp.t2, src, n, id_bits, tile, range.x, colors, g, b);
-        else if (n <= 1024) TileSort<4>::run(temp.t4, src, n, id_bits, tile, range.x, colors, g, b);
-        else TileSort<8>::run(temp.t8, src, n, id_bits, tile, range.x, colors, g, b);
+        if (n <= 512) TileSort<2>::run(temp.t2, flags, src, n, id_bits, tile, range.x, colors, g, b);
+        else if (n <= 1024) TileSort<4>::run(temp.t4, flags, src, n, id_bits, tile, range.x, colors, g, b);
+        else TileSort<8>::run(temp.t8, flags, src, n, id_bits, tile, range.x, colors, g, b);
     }
 }
 

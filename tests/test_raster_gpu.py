@@ -283,3 +283,16 @@ def test_planned_sync_free_forward_and_cuda_graph():
     pr.replay(); pr.replay()
     torch.cuda.synchronize()
     assert pr.ok() and torch.equal(pr.color, ref.color)
+
+
+@pytest.mark.parametrize("base_P,rep", [(1500, 3), (120, 40)])
+def test_equal_depth_runs_are_ordered_by_gaussian_index(base_P, rep):
+    """Exact depth ties (identical positions): the in-CTA sort orders equal-depth runs by Gaussian id with a shared-memory
+    fix-up (runs <= 16) or the full radix fallback (longer runs) -- both must reproduce the stable (tile, depth) order."""
+    sc = synth.random_cube_scene(base_P, 96, spread=0.5, scale_mul=2.0, seed=21, bg=(0.1, 0.1, 0.1))
+    for k in ("means3D", "colors", "opacity", "scales", "rots"):
+        sc[k] = np.ascontiguousarray(np.repeat(sc[k], rep, axis=0))
+    perm = np.random.default_rng(0).permutation(base_P * rep)       # interleave the duplicates in index space
+    for k in ("means3D", "colors", "opacity", "scales", "rots"):
+        sc[k] = np.ascontiguousarray(sc[k][perm])
+    _assert_forward_parity(sc)
