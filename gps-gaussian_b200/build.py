@@ -27,6 +27,7 @@ SOURCES = {
     "raster_render.cu": [],
     "raster_backward.cu": [],
     "corr.cu": [],
+    "sh.cu": [],
 }
 
 

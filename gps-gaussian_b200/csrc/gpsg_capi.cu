@@ -193,9 +193,11 @@ int gpsg_rasterize_forward(const GpsgRasterSettings* s, int device, void* stream
                      "Please provide excatly one of either SHs or precomputed colors!");
         GPSG_REQUIRE(((scales != nullptr && rotations != nullptr) != (cov3D_precomp != nullptr)),
                      "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
-        GPSG_REQUIRE(shs == nullptr, "SH colour path is not built yet (GPS-Gaussian passes colors_precomp)");
+        if (shs) {
+            GPSG_REQUIRE(s->sh_degree >= 0 && s->sh_degree <= 3, "sh_degree must be 0..3");
+            GPSG_REQUIRE(sh_M >= (s->sh_degree + 1) * (s->sh_degree + 1), "shs has fewer coefficients than (sh_degree+1)^2");
+        }
     }
-    (void)sh_M;
     cudaStream_t stream = (cudaStream_t)stream_;
     GPSG_CUDA(cudaSetDevice(device));
     const Camera cam = make_camera(*s);
@@ -228,6 +230,11 @@ int gpsg_rasterize_forward(const GpsgRasterSettings* s, int device, void* stream
         max_count = slot[1];
     }
     if (num_rendered) *num_rendered = (int32_t)N;
+    if (shs && P > 0) {   // SH -> RGB for the visible Gaussians (kept in the geometry buffer for the backward)
+        rc = launch_sh_forward(P, s->sh_degree, sh_M, s->campos, means3D, shs, radii, g.rgb, g.clamped, stream);
+        if (rc) return rc;
+        colors_precomp = g.rgb;
+    }
 
     const bool radix_path = max_count > kMaxTileSort || force_radix_binning();
     const int end_bit = 32 + bit_length((uint32_t)tiles);
@@ -302,7 +309,10 @@ int gpsg_rasterize_forward_planned(const GpsgRasterSettings* s, int device, void
     return rc;
 }
 
-size_t gpsg_rasterize_backward_workspace_bytes(int P) { return align_up(sizeof(float4) * (size_t)(P > 0 ? P : 1)) + 256; }
+size_t gpsg_rasterize_backward_workspace_bytes(int P) {
+    const size_t n = (size_t)(P > 0 ? P : 1);
+    return align_up(sizeof(float4) * n) + align_up(sizeof(float) * 3 * n) + 256;   // dL_dconic+opacity, dL_dcolors (SH path)
+}
 
 int gpsg_rasterize_backward(const GpsgRasterSettings* s, int device, void* stream_, int P, int sh_M,
                             int32_t num_rendered, const float* means3D, const float* colors_precomp, const float* shs,
@@ -317,17 +327,18 @@ int gpsg_rasterize_backward(const GpsgRasterSettings* s, int device, void* strea
     if (P == 0) return GPSG_OK;
     GPSG_REQUIRE(means3D && radii && geom_buffer && binning_buffer && image_buffer && dL_dout_color,
                  "a required input pointer is NULL");
-    GPSG_REQUIRE(dL_dmeans2D && dL_dcolors && dL_dopacity && dL_dmeans3D && workspace,
-                 "a required output pointer is NULL");
-    GPSG_REQUIRE(shs == nullptr && dL_dsh == nullptr, "SH colour path is not built yet");
+    GPSG_REQUIRE(dL_dmeans2D && dL_dopacity && dL_dmeans3D && workspace, "a required output pointer is NULL");
+    GPSG_REQUIRE((shs != nullptr) == (dL_dsh != nullptr), "dL_dsh must be given exactly when shs is");
+    GPSG_REQUIRE(shs != nullptr || dL_dcolors != nullptr, "dL_dcolors is NULL");
     GPSG_REQUIRE((scales && rotations) || cov3D_precomp, "need scales+rotations or cov3D_precomp");
-    (void)sh_M; (void)colors_precomp; (void)opacities;
+    (void)colors_precomp; (void)opacities;
     cudaStream_t stream = (cudaStream_t)stream_;
     GPSG_CUDA(cudaSetDevice(device));
     const Camera cam = make_camera(*s);
     BinningState b = BinningState::carve(const_cast<void*>(binning_buffer), (size_t)num_rendered, 0);
     ImageState im = ImageState::carve(const_cast<void*>(image_buffer), cam.W, cam.H);
     float4* dconic_op = (float4*)align_up((size_t)workspace);
+    if (!dL_dcolors) dL_dcolors = (float*)((char*)dconic_op + align_up(sizeof(float4) * (size_t)P));   // SH path scratch
     GPSG_CUDA(cudaMemsetAsync(dL_dmeans2D, 0, sizeof(float) * 3 * (size_t)P, stream));
     GPSG_CUDA(cudaMemsetAsync(dL_dcolors, 0, sizeof(float) * 3 * (size_t)P, stream));
     GPSG_CUDA(cudaMemsetAsync(dconic_op, 0, sizeof(float4) * (size_t)P, stream));
@@ -342,6 +353,12 @@ int gpsg_rasterize_backward(const GpsgRasterSettings* s, int device, void* strea
                                     dL_dopacity, dL_dmeans3D, dL_dcov3D, cov3D_precomp ? nullptr : dL_dscales,
                                     cov3D_precomp ? nullptr : dL_drotations, stream); }
     if (rc) return rc;
+    if (shs) {
+        GeomState g = GeomState::carve(const_cast<void*>(geom_buffer), P, 0);
+        rc = launch_sh_backward(P, s->sh_degree, sh_M, s->campos, means3D, shs, radii, g.clamped, dL_dcolors, dL_dsh,
+                                dL_dmeans3D, stream);
+        if (rc) return rc;
+    }
     if (cov3D_precomp) {
         if (dL_dscales) GPSG_CUDA(cudaMemsetAsync(dL_dscales, 0, sizeof(float) * 3 * (size_t)P, stream));
         if (dL_drotations) GPSG_CUDA(cudaMemsetAsync(dL_drotations, 0, sizeof(float) * 4 * (size_t)P, stream));

@@ -115,6 +115,12 @@ int launch_preprocess_backward(const Camera& cam, int P, const float* means3D, c
                                const float* dL_dmeans2D, const float4* dL_dconic_op, float* dL_dopacity,
                                float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales, float* dL_drots,
                                cudaStream_t stream);
+// sh.cu
+int launch_sh_forward(int P, int deg, int M, const float* campos3, const float* means3D, const float* shs,
+                      const int32_t* radii, float* rgb, uint8_t* clamped, cudaStream_t stream);
+int launch_sh_backward(int P, int deg, int M, const float* campos3, const float* means3D, const float* shs,
+                       const int32_t* radii, const uint8_t* clamped, const float* dL_dcolors, float* dL_dsh,
+                       float* dL_dmeans3D, cudaStream_t stream);
 // corr.cu
 int launch_corr_fwd(int dtype, int B, int H, int W1, int W2, const void* vol, int64_t sb, int64_t sh, int64_t sw1,
                     const float* coords, int64_t csb, int r, void* out, cudaStream_t stream);

@@ -135,6 +135,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         d_means2D, d_colors, d_opacity, d_means3D = new(P, 3), new(P, 3), new(P, 1), new(P, 3)
         d_scales, d_rots = new(P, 3), new(P, 4)
         d_cov3D = new(P, 6) if has_cp else None
+        d_sh = new(P, sh_M, 3) if has_sh else None
         ws = torch.empty(int(_lib.lib.gpsg_rasterize_backward_workspace_bytes(P)), dtype=torch.uint8, device=dev)
         geom, binning, image = ctx.bufs
         if P > 0:
@@ -144,11 +145,11 @@ class _RasterizeGaussians(torch.autograd.Function):
                     _stream(dev), P, sh_M, ctx.num_rendered, _ptr(m3), _ptr(col) if has_col else None,
                     _ptr(shs) if has_sh else None, _ptr(op), _ptr(sc) if has_sc else None,
                     _ptr(ro) if has_ro else None, _ptr(cp) if has_cp else None, _ptr(radii), _ptr(geom),
-                    _ptr(binning), _ptr(image), _ptr(g), _ptr(d_means2D), _ptr(d_colors), _ptr(d_opacity),
-                    _ptr(d_means3D), _ptr(d_cov3D), None, _ptr(d_scales), _ptr(d_rots), _ptr(ws))
+                    _ptr(binning), _ptr(image), _ptr(g), _ptr(d_means2D), _ptr(d_colors) if has_col else None,
+                    _ptr(d_opacity), _ptr(d_means3D), _ptr(d_cov3D), _ptr(d_sh), _ptr(d_scales), _ptr(d_rots), _ptr(ws))
             _lib.check(rc, "gpsg_rasterize_backward")
         # input order: means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, settings
-        return (d_means3D, d_means2D, None, d_colors if has_col else None, d_opacity,
+        return (d_means3D, d_means2D, d_sh, d_colors if has_col else None, d_opacity,
                 d_scales if has_sc else None, d_rots if has_ro else None, d_cov3D, None)
 
 

@@ -451,6 +451,101 @@ void SUFFIX(oracle_preprocess_backward)(int P, int W, int H, const real* means3D
     }
 }
 
+
+/* ------------------------------------------------------------------ SH colours (A.2 step 9 / A.8) */
+/* Real spherical harmonics up to degree 3, the basis constants published with 3D Gaussian Splatting
+ * (upstream forward.cu::computeColorFromSH / backward.cu::computeColorFromSH).  GPS-Gaussian never uses this
+ * branch (it passes colors_precomp, reference gaussian_renderer/__init__.py:57-58); kept for API completeness. */
+static const double kC0 = 0.28209479177387814, kC1 = 0.4886025119029199;
+static const double kC2[5] = {1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396};
+static const double kC3[7] = {-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154,
+                              -0.4570457994644658, 1.445305721320277, -0.5900435899266435};
+
+/* basis b[16] and its gradient wrt the unit direction (x,y,z): db[k][3] */
+static void sh_basis(int deg, real x, real y, real z, real* b, real (*db)[3]) {
+    for (int k = 0; k < 16; ++k) { b[k] = 0; if (db) db[k][0] = db[k][1] = db[k][2] = 0; }
+    b[0] = (real)kC0;
+    if (deg < 1) return;
+    b[1] = -(real)kC1 * y; b[2] = (real)kC1 * z; b[3] = -(real)kC1 * x;
+    if (db) { db[1][1] = -(real)kC1; db[2][2] = (real)kC1; db[3][0] = -(real)kC1; }
+    if (deg < 2) return;
+    real xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    b[4] = (real)kC2[0] * xy; b[5] = (real)kC2[1] * yz; b[6] = (real)kC2[2] * (RC(2.0) * zz - xx - yy);
+    b[7] = (real)kC2[3] * xz; b[8] = (real)kC2[4] * (xx - yy);
+    if (db) {
+        db[4][0] = (real)kC2[0] * y; db[4][1] = (real)kC2[0] * x;
+        db[5][1] = (real)kC2[1] * z; db[5][2] = (real)kC2[1] * y;
+        db[6][0] = (real)kC2[2] * (-RC(2.0) * x); db[6][1] = (real)kC2[2] * (-RC(2.0) * y); db[6][2] = (real)kC2[2] * (RC(4.0) * z);
+        db[7][0] = (real)kC2[3] * z; db[7][2] = (real)kC2[3] * x;
+        db[8][0] = (real)kC2[4] * (RC(2.0) * x); db[8][1] = (real)kC2[4] * (-RC(2.0) * y);
+    }
+    if (deg < 3) return;
+    b[9] = (real)kC3[0] * y * (RC(3.0) * xx - yy);
+    b[10] = (real)kC3[1] * xy * z;
+    b[11] = (real)kC3[2] * y * (RC(4.0) * zz - xx - yy);
+    b[12] = (real)kC3[3] * z * (RC(2.0) * zz - RC(3.0) * xx - RC(3.0) * yy);
+    b[13] = (real)kC3[4] * x * (RC(4.0) * zz - xx - yy);
+    b[14] = (real)kC3[5] * z * (xx - yy);
+    b[15] = (real)kC3[6] * x * (xx - RC(3.0) * yy);
+    if (db) {
+        db[9][0] = (real)kC3[0] * RC(6.0) * xy;            db[9][1] = (real)kC3[0] * (RC(3.0) * xx - RC(3.0) * yy);
+        db[10][0] = (real)kC3[1] * yz; db[10][1] = (real)kC3[1] * xz; db[10][2] = (real)kC3[1] * xy;
+        db[11][0] = (real)kC3[2] * (-RC(2.0) * xy); db[11][1] = (real)kC3[2] * (RC(4.0) * zz - xx - RC(3.0) * yy); db[11][2] = (real)kC3[2] * RC(8.0) * yz;
+        db[12][0] = (real)kC3[3] * (-RC(6.0) * xz); db[12][1] = (real)kC3[3] * (-RC(6.0) * yz); db[12][2] = (real)kC3[3] * (RC(6.0) * zz - RC(3.0) * xx - RC(3.0) * yy);
+        db[13][0] = (real)kC3[4] * (RC(4.0) * zz - RC(3.0) * xx - yy); db[13][1] = (real)kC3[4] * (-RC(2.0) * xy); db[13][2] = (real)kC3[4] * RC(8.0) * xz;
+        db[14][0] = (real)kC3[5] * RC(2.0) * xz; db[14][1] = (real)kC3[5] * (-RC(2.0) * yz); db[14][2] = (real)kC3[5] * (xx - yy);
+        db[15][0] = (real)kC3[6] * (RC(3.0) * xx - RC(3.0) * yy); db[15][1] = (real)kC3[6] * (-RC(6.0) * xy);
+    }
+}
+
+/* colours[P,3] = max(0, sum_k b_k(dir) sh[P,M,3] + 0.5), clamped[P,3] = (value < 0); dir = normalize(mean - campos) */
+void SUFFIX(oracle_sh_forward)(int P, int deg, int M, const real* means3D, const real* campos, const real* shs,
+                               real* colors, uint8_t* clamped) {
+    const int nb = (deg + 1) * (deg + 1);
+    for (int i = 0; i < P; ++i) {
+        real dx = means3D[3 * i] - campos[0], dy = means3D[3 * i + 1] - campos[1], dz = means3D[3 * i + 2] - campos[2];
+        real inv = RC(1.0) / R_SQRT(dx * dx + dy * dy + dz * dz);
+        real b[16];
+        sh_basis(deg, dx * inv, dy * inv, dz * inv, b, 0);
+        for (int c = 0; c < 3; ++c) {
+            real v = 0;
+            for (int k = 0; k < nb; ++k) v += b[k] * shs[((size_t)i * M + k) * 3 + c];
+            v += RC(0.5);
+            clamped[3 * i + c] = v < 0;
+            colors[3 * i + c] = v < 0 ? 0 : v;
+        }
+    }
+}
+
+/* dL_dcolors[P,3] -> dL_dsh[P,M,3] and the view-direction term ADDED to dL_dmeans3D[P,3] */
+void SUFFIX(oracle_sh_backward)(int P, int deg, int M, const real* means3D, const real* campos, const real* shs,
+                                const uint8_t* clamped, const real* dL_dcolors, real* dL_dsh, real* dL_dmeans3D) {
+    const int nb = (deg + 1) * (deg + 1);
+    memset(dL_dsh, 0, sizeof(real) * (size_t)P * M * 3);
+    for (int i = 0; i < P; ++i) {
+        real v[3] = {means3D[3 * i] - campos[0], means3D[3 * i + 1] - campos[1], means3D[3 * i + 2] - campos[2]};
+        real len2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+        real inv = RC(1.0) / R_SQRT(len2);
+        real d[3] = {v[0] * inv, v[1] * inv, v[2] * inv};
+        real b[16], db[16][3];
+        sh_basis(deg, d[0], d[1], d[2], b, db);
+        real g[3];
+        for (int c = 0; c < 3; ++c) g[c] = clamped[3 * i + c] ? 0 : dL_dcolors[3 * i + c];
+        real ddir[3] = {0, 0, 0};
+        for (int k = 0; k < nb; ++k) {
+            real dot = 0;
+            for (int c = 0; c < 3; ++c) {
+                dL_dsh[((size_t)i * M + k) * 3 + c] = b[k] * g[c];
+                dot += shs[((size_t)i * M + k) * 3 + c] * g[c];
+            }
+            for (int a = 0; a < 3; ++a) ddir[a] += db[k][a] * dot;
+        }
+        /* through the normalisation d = v/|v| :  dv = (ddir - d (d . ddir)) / |v| */
+        real dd = d[0] * ddir[0] + d[1] * ddir[1] + d[2] * ddir[2];
+        for (int a = 0; a < 3; ++a) dL_dmeans3D[3 * i + a] += (ddir[a] - d[a] * dd) * inv;
+    }
+}
+
 /* ------------------------------------------------------------------ mark_visible (N12) */
 void SUFFIX(oracle_mark_visible)(int P, const real* means3D, const real* view, uint8_t* present) {
     for (int i = 0; i < P; ++i) {

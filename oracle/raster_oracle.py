@@ -58,6 +58,25 @@ class RasterOracle:
     def max_threads(self):
         return int(self._fn("oracle_max_threads")())
 
+    def sh_colors(self, means3D, campos, shs, deg):
+        """SH -> RGB (+0.5, clamp at 0).  shs: [P, M, 3].  Returns (colors[P,3], clamped[P,3] bool)."""
+        shs = self._a(shs); P, M = shs.shape[0], shs.shape[1]
+        m3 = self._a(means3D, (P, 3)); cp = self._a(campos, (3,))
+        col = np.zeros((P, 3), self.np); cl = np.zeros((P, 3), np.uint8)
+        self._fn("oracle_sh_forward")(C.c_int(P), C.c_int(deg), C.c_int(M), _p(m3), _p(cp), _p(shs), _p(col), _p(cl))
+        return col, cl
+
+    def sh_backward(self, means3D, campos, shs, deg, clamped, dL_dcolors, dL_dmeans3D):
+        """Returns dL_dsh[P,M,3]; ADDS the view-direction term into dL_dmeans3D (in place)."""
+        shs = self._a(shs); P, M = shs.shape[0], shs.shape[1]
+        m3 = self._a(means3D, (P, 3)); cp = self._a(campos, (3,)); g = self._a(dL_dcolors, (P, 3))
+        cl = np.ascontiguousarray(clamped, np.uint8)
+        dsh = np.zeros((P, M, 3), self.np)
+        assert dL_dmeans3D.dtype == self.np and dL_dmeans3D.flags.c_contiguous
+        self._fn("oracle_sh_backward")(C.c_int(P), C.c_int(deg), C.c_int(M), _p(m3), _p(cp), _p(shs), _p(cl), _p(g), _p(dsh),
+                                       _p(dL_dmeans3D))
+        return dsh
+
     def forward(self, means3D, colors, opacity, scales, rots, view, proj, tanfovx, tanfovy, W, H, bg,
                 scale_mod=1.0, cov3D_precomp=None, nthreads=1, render=True):
         """view/proj: the 4x4 tensors exactly as the reference passes them (row-vector convention,

@@ -296,3 +296,38 @@ def test_equal_depth_runs_are_ordered_by_gaussian_index(base_P, rep):
     for k in ("means3D", "colors", "opacity", "scales", "rots"):
         sc[k] = np.ascontiguousarray(sc[k][perm])
     _assert_forward_parity(sc)
+
+
+@pytest.mark.parametrize("deg,M", [(3, 16), (1, 4), (0, 16)])
+def test_sh_colour_branch_forward_backward(deg, M):
+    """`GaussianRasterizer(shs=...)`: SH->RGB (+0.5, clamp) in front of the rasterizer and its backward (dL_dsh and the
+    view-direction term of dL_dmeans3D).  Not used by GPS-Gaussian (it passes colors_precomp); API completeness."""
+    import diff_gaussian_rasterization as dgr
+    P, res = 4000, 128
+    sc = synth.random_cube_scene(P, res, seed=17, bg=(0.1, 0.2, 0.3), scale_mul=2.0)
+    rng = np.random.default_rng(5)
+    shs = (rng.standard_normal((P, M, 3)) * 0.5).astype(np.float32)
+    o = RasterOracleF64 = None
+    from oracle.raster_oracle import RasterOracle
+    o = RasterOracle("f64")
+    col, cl = o.sh_colors(sc["means3D"], sc["campos"], shs, deg)
+    assert 0.05 < cl.mean() < 0.95 or deg == 0                                   # the clamp is exercised
+    sc_o = dict(sc, colors=col)
+    _, ref = oracle_forward(sc_o, "f64")
+    T = lambda a: torch.tensor(a, device="cuda", requires_grad=True)
+    m, sh_t, op, s_, r = T(sc["means3D"]), T(shs), T(sc["opacity"]), T(sc["scales"]), T(sc["rots"])
+    rs = dgr.GaussianRasterizationSettings(
+        image_height=res, image_width=res, tanfovx=sc["tanfovx"], tanfovy=sc["tanfovy"], bg=torch.tensor(sc["bg"]),
+        scale_modifier=1.0, viewmatrix=torch.tensor(sc["view"]), projmatrix=torch.tensor(sc["proj"]), sh_degree=deg,
+        campos=torch.tensor(sc["campos"]), prefiltered=False, debug=False)
+    img, radii = dgr.GaussianRasterizer(raster_settings=rs)(means3D=m, means2D=torch.zeros_like(m), opacities=op, shs=sh_t,
+                                                            colors_precomp=None, scales=s_, rotations=r, cov3D_precomp=None)
+    d = np.abs(_np(img) - ref["color"]).max(0)
+    assert (d > RGB_TOL).mean() < 1e-3 and d.max() < 1e-2
+    g = rng.standard_normal((3, res, res)).astype(np.float32)
+    img.backward(torch.from_numpy(g).cuda())
+    want = o.backward(ref, g.astype(np.float64))
+    dsh = o.sh_backward(sc["means3D"], sc["campos"], shs, deg, cl, want["dL_dcolors"], want["dL_dmeans3D"])   # adds dir term
+    for got, exp in ((sh_t.grad, dsh), (m.grad, want["dL_dmeans3D"]), (op.grad, want["dL_dopacity"]), (s_.grad, want["dL_dscales"])):
+        per = _grad_err(_np(got), exp)
+        assert int((per > GRAD_TOL).sum()) <= max(2, int(1e-3 * P)) and per.max() < 5e-2
