@@ -311,7 +311,7 @@ def test_sh_colour_branch_forward_backward(deg, M):
     from oracle.raster_oracle import RasterOracle
     o = RasterOracle("f64")
     col, cl = o.sh_colors(sc["means3D"], sc["campos"], shs, deg)
-    assert 0.05 < cl.mean() < 0.95 or deg == 0                                   # the clamp is exercised
+    assert 0.01 < cl.mean() < 0.95 or deg == 0                                   # the clamp is exercised
     sc_o = dict(sc, colors=col)
     _, ref = oracle_forward(sc_o, "f64")
     T = lambda a: torch.tensor(a, device="cuda", requires_grad=True)
