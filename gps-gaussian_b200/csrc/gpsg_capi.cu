@@ -348,8 +348,10 @@ int gpsg_rasterize_backward(const GpsgRasterSettings* s, int device, void* strea
         if (rc) return rc;
     }
     { StageTimer t(ST_PREPROCESS_BWD, stream, 1);
+    GeomState gst = GeomState::carve(const_cast<void*>(geom_buffer), P, 0);
     rc = launch_preprocess_backward(cam, P, means3D, radii, cov3D_precomp ? nullptr : scales,
-                                    cov3D_precomp ? nullptr : rotations, cov3D_precomp, dL_dmeans2D, dconic_op,
+                                    cov3D_precomp ? nullptr : rotations, cov3D_precomp, gst.conic_opacity, dL_dmeans2D,
+                                    dconic_op,
                                     dL_dopacity, dL_dmeans3D, dL_dcov3D, cov3D_precomp ? nullptr : dL_dscales,
                                     cov3D_precomp ? nullptr : dL_drotations, stream); }
     if (rc) return rc;

@@ -112,9 +112,9 @@ int launch_render_backward(const Camera& cam, BinningState b, ImageState im, con
                            float* dL_dcolors /*[P,3]*/, cudaStream_t stream);
 int launch_preprocess_backward(const Camera& cam, int P, const float* means3D, const int32_t* radii,
                                const float* scales, const float* rots, const float* cov3D_precomp,
-                               const float* dL_dmeans2D, const float4* dL_dconic_op, float* dL_dopacity,
-                               float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales, float* dL_drots,
-                               cudaStream_t stream);
+                               const float4* conic_opacity, float* dL_dmeans2D /* in: moments, out: gradient */,
+                               const float4* dL_dconic_op /* moments */, float* dL_dopacity, float* dL_dmeans3D,
+                               float* dL_dcov3D, float* dL_dscales, float* dL_drots, cudaStream_t stream);
 // sh.cu
 int launch_sh_forward(int P, int deg, int M, const float* campos3, const float* means3D, const float* shs,
                       const int32_t* radii, float* rgb, uint8_t* clamped, cudaStream_t stream);

@@ -126,16 +126,16 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32) render_backward_kernel(c
                         dL_dalpha *= T;
                         last_alpha = alpha;
                         dL_dalpha = fmaf(-T_final * inv1ma, bg_dot, dL_dalpha);
-                        const float dL_dG = q.w * dL_dalpha;
-                        // conic = (-2 ln2 Bx, -ln2 By, -2 ln2 Bz): dG/ddelx = -G (cx dx + cy dy) = ln2 G (2 Bx dx + By dy)
-                        const float gl = kLn2 * G * dL_dG;
-                        xo[0] = gl * fmaf(2.0f * q.x, dx, q.y * dy) * ddelx_dx;
-                        xo[1] = gl * fmaf(2.0f * q.z, dy, q.y * dx) * ddely_dy;
-                        const float h = -0.5f * G * dL_dG;
-                        xo[2] = h * dx * dx;
-                        xo[3] = h * dx * dy;
-                        xo[4] = h * dy * dy;
-                        xo[5] = G * dL_dalpha;
+                        // Raw moments of s = G * dL/dG over the pixels (converted to d/dmean2D, d/dconic, d/dopacity once
+                        // per Gaussian in preprocess_backward):  xo[0..5] = s * (dx, dy, dx^2, dx*dy, dy^2, 1)
+                        const float sG = G * (q.w * dL_dalpha);
+                        const float sx = sG * dx, sy = sG * dy;
+                        xo[0] = sx;
+                        xo[1] = sy;
+                        xo[2] = sx * dx;
+                        xo[3] = sx * dy;
+                        xo[4] = sy * dy;
+                        xo[5] = sG;
                     }
                 }
                 return active;
@@ -212,20 +212,29 @@ int launch_render_backward(const Camera& cam, BinningState b, ImageState im, con
 __global__ void __launch_bounds__(256) preprocess_backward_kernel(
     const __grid_constant__ Camera cam, int P, const float* __restrict__ means3D, const int32_t* __restrict__ radii,
     const float* __restrict__ scales, const float* __restrict__ rots, const float* __restrict__ cov3D_precomp,
-    const float* __restrict__ dL_dmeans2D, const float4* __restrict__ dL_dconic_op, float* __restrict__ dL_dopacity,
+    const float4* __restrict__ conic_opacity, const float* dL_dmeans2D, float* dL_dmeans2D_out,
+    const float4* __restrict__ dL_dconic_op, float* __restrict__ dL_dopacity,
     float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dscales,
     float* __restrict__ dL_drots) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     float dm[3] = {0.f, 0.f, 0.f}, dsc[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float dop = 0.f;
+    float dop = 0.f, dm2[2] = {0.f, 0.f};
     if (radii[i] > 0) {
         const float* view = cam.view;
         const float* proj = cam.proj;
         const float x = means3D[3 * i], y = means3D[3 * i + 1], z = means3D[3 * i + 2];
-        const float4 gco = dL_dconic_op[i];
-        dop = gco.w;
+        // The compositing backward accumulated raw moments of s = G*dL/dG (see render_backward_kernel):
+        //   dL_dmeans2D[i] = (sum s*dx, sum s*dy), dL_dconic_op[i] = (sum s*dx^2, sum s*dx*dy, sum s*dy^2, sum s).
+        // With conic (cx,cy,cz) and opacity o:  dG/ddelx = -G (cx dx + cy dy), dG/dcx = -G dx^2 / 2, ...
+        const float4 mom = dL_dconic_op[i];
+        const float4 co = conic_opacity[i];
+        const float m1x = dL_dmeans2D[3 * i], m1y = dL_dmeans2D[3 * i + 1];
+        const float4 gco = make_float4(-0.5f * mom.x, -0.5f * mom.y, -0.5f * mom.z, 0.f);
+        dop = co.w != 0.f ? mom.w / co.w : 0.f;
+        const float gm0_ = -(co.x * m1x + co.y * m1y) * (0.5f * (float)cam.W);
+        const float gm1_ = -(co.z * m1y + co.y * m1x) * (0.5f * (float)cam.H);
         // --- Sigma3D (recomputed; not stored by the forward) ---
         float c6[6];
         float R[3][3];
@@ -322,7 +331,8 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
         const float m_w = 1.0f / (hw + 0.0000001f);
         const float mul1 = (proj[0] * x + proj[4] * y + proj[8] * z + proj[12]) * m_w * m_w;
         const float mul2 = (proj[1] * x + proj[5] * y + proj[9] * z + proj[13]) * m_w * m_w;
-        const float gm0 = dL_dmeans2D[3 * i], gm1 = dL_dmeans2D[3 * i + 1];
+        const float gm0 = gm0_, gm1 = gm1_;
+        dm2[0] = gm0; dm2[1] = gm1;
         dm[0] += (proj[0] * m_w - proj[3] * mul1) * gm0 + (proj[1] * m_w - proj[3] * mul2) * gm1;
         dm[1] += (proj[4] * m_w - proj[7] * mul1) * gm0 + (proj[5] * m_w - proj[7] * mul2) * gm1;
         dm[2] += (proj[8] * m_w - proj[11] * mul1) * gm0 + (proj[9] * m_w - proj[11] * mul2) * gm1;
@@ -353,6 +363,8 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
         }
     }
     dL_dopacity[i] = dop;
+    dL_dmeans2D_out[3 * i] = dm2[0];      // final d/dmeans2D (NDC-scaled, as upstream) replaces the moment scratch
+    dL_dmeans2D_out[3 * i + 1] = dm2[1];
 #pragma unroll
     for (int k = 0; k < 3; ++k) dL_dmeans3D[3 * i + k] = dm[k];
     if (dL_dcov3D) {
@@ -371,12 +383,13 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
 
 int launch_preprocess_backward(const Camera& cam, int P, const float* means3D, const int32_t* radii,
                                const float* scales, const float* rots, const float* cov3D_precomp,
-                               const float* dL_dmeans2D, const float4* dL_dconic_op, float* dL_dopacity,
-                               float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales, float* dL_drots,
-                               cudaStream_t stream) {
+                               const float4* conic_opacity, float* dL_dmeans2D, const float4* dL_dconic_op,
+                               float* dL_dopacity, float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales,
+                               float* dL_drots, cudaStream_t stream) {
     if (P <= 0) return GPSG_OK;
     preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(cam, P, means3D, radii, scales, rots,
-                                                                   cov3D_precomp, dL_dmeans2D, dL_dconic_op,
+                                                                   cov3D_precomp, conic_opacity, dL_dmeans2D,
+                                                                   dL_dmeans2D, dL_dconic_op,
                                                                    dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dscales,
                                                                    dL_drots);
     GPSG_LAUNCH_CHECK();

@@ -82,24 +82,26 @@ __global__ void __launch_bounds__((kFwdWarps + 1) * 32) render_forward_kernel(co
                 while (m) {
                     const int j = base + __ffs(m) - 1;
                     m &= m - 1;
-                    if (done) continue;
+                    // Straight-line, predicated evaluation: under SIMT the "contributing" tail runs whenever ANY lane
+                    // contributes (almost always for a survivor), so per-lane branches only add BSSY/BSYNC/BRA overhead.
                     const float2 xy = *reinterpret_cast<const float2*>(&SA[j]);
                     const float4 q = SB[j];
+                    const float4 c = SC[j];
                     const float dx = xy.x - pixfx, dy = xy.y - pixfy;
                     // p = log2e * power,  power = -0.5*(cx dx^2 + cz dy^2) - cy dx dy
                     const float p = fmaf(q.z * dy, dy, fmaf(q.x, dx, q.y * dy) * dx);
-                    if (p > 0.0f) continue;
                     const float alpha = fminf(0.99f, q.w * ex2_approx(p));
-                    if (alpha < 1.0f / 255.0f) continue;
+                    const bool valid = !done && !(p > 0.0f) && !(alpha < 1.0f / 255.0f);
                     const float test_T = T * (1.0f - alpha);
-                    if (test_T < 0.0001f) { done = true; continue; }
-                    const float4 c = SC[j];
-                    const float w = alpha * T;
+                    const bool stop = valid && (test_T < 0.0001f);
+                    const bool upd = valid && !stop;
+                    done = done || stop;
+                    const float w = upd ? alpha * T : 0.0f;
                     C0 = fmaf(c.x, w, C0);
                     C1 = fmaf(c.y, w, C1);
                     C2 = fmaf(c.z, w, C2);
-                    T = test_T;
-                    last_contributor = posbase + j;
+                    T = upd ? test_T : T;
+                    last_contributor = upd ? posbase + j : last_contributor;
                 }
                 if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
             }
