@@ -101,8 +101,9 @@ static ImageState carve_image(char* p, int W, int H, char** end) {
     im.n_contrib = take<uint32_t>(p, hw > 0 ? hw : 1);
     im.ranges = take<uint2>(p, tiles > 0 ? tiles : 1);
     im.tile_count = take<uint32_t>(p, tiles > 0 ? tiles : 1);
+    im.totals = take<uint32_t>(p, 64);            // directly after tile_count: one memset clears both
     im.tile_cursor = take<uint32_t>(p, tiles > 0 ? tiles : 1);
-    im.totals = take<uint32_t>(p, 64);
+    im.big_tiles = take<uint32_t>(p, tiles > 0 ? tiles : 1);
     if (end) *end = p;
     return im;
 }
@@ -214,13 +215,14 @@ int gpsg_rasterize_forward(const GpsgRasterSettings* s, int device, void* stream
     // ---- per-Gaussian projection + pairs-per-tile counts, then tile ranges; one host read: (N, max tile count)
     uint32_t N = 0, max_count = 0;
     int rc = GPSG_OK;
-    GPSG_CUDA(cudaMemsetAsync(im.tile_count, 0, sizeof(uint32_t) * (size_t)tiles, stream));
-    if (P > 0) {
-        { StageTimer t(ST_PREPROCESS, stream, 1); rc = launch_preprocess(cam, P, means3D, scales, rotations, opacities, cov3D_precomp, radii, g, im.tile_count, stream); }
+    GPSG_CUDA(cudaMemsetAsync(im.tile_count, 0, (size_t)((char*)(im.totals + 64) - (char*)im.tile_count), stream));
+    if (P > 0) {   // projection + pairs-per-tile histogram; its last CTA also scans the histogram into tile ranges
+        { StageTimer t(ST_PREPROCESS, stream, 1); rc = launch_preprocess(cam, P, means3D, scales, rotations, opacities, cov3D_precomp, radii, g, im, 0u, stream); }
+        if (rc) return rc;
+    } else {
+        { StageTimer t(ST_TILE_SCAN, stream, 1); rc = launch_tile_scan(cam, im, 0u, stream); }
         if (rc) return rc;
     }
-    { StageTimer t(ST_TILE_SCAN, stream, 1); rc = launch_tile_scan(cam, im, 0u, stream); }
-    if (rc) return rc;
     if (P > 0) {
         uint32_t* slot = pinned_slot();
         GPSG_REQUIRE(slot != nullptr, "cudaHostAlloc failed");
@@ -293,12 +295,9 @@ int gpsg_rasterize_forward_planned(const GpsgRasterSettings* s, int device, void
     GeomState g = GeomState::carve(geom_buffer, P, 0);
     ImageState im = ImageState::carve(image_buffer, cam.W, cam.H);
     BinningState b = BinningState::carve(binning_buffer, (size_t)capacity_pairs, 0);
-    const int tiles = cam.grid_x * cam.grid_y;
     int rc = GPSG_OK;
-    GPSG_CUDA(cudaMemsetAsync(im.tile_count, 0, sizeof(uint32_t) * (size_t)tiles, stream));
-    { StageTimer t(ST_PREPROCESS, stream, 1); rc = launch_preprocess(cam, P, means3D, scales, rotations, opacities, cov3D_precomp, radii, g, im.tile_count, stream); }
-    if (rc) return rc;
-    { StageTimer t(ST_TILE_SCAN, stream, 1); rc = launch_tile_scan(cam, im, (uint32_t)capacity_pairs, stream); }
+    GPSG_CUDA(cudaMemsetAsync(im.tile_count, 0, (size_t)((char*)(im.totals + 64) - (char*)im.tile_count), stream));
+    { StageTimer t(ST_PREPROCESS, stream, 1); rc = launch_preprocess(cam, P, means3D, scales, rotations, opacities, cov3D_precomp, radii, g, im, (uint32_t)capacity_pairs, stream); }
     if (rc) return rc;
     if (status_host) GPSG_CUDA(cudaMemcpyAsync(status_host, im.totals, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     { StageTimer t(ST_SCATTER, stream, 1); rc = launch_bucket_scatter(cam, P, radii, g, b, im, stream); }

@@ -78,7 +78,8 @@ struct ImageState {
     uint2* ranges;        // [tiles]
     uint32_t* tile_count; // [tiles]  pairs per tile (counted by preprocess)
     uint32_t* tile_cursor;// [tiles]  scatter cursors
-    uint32_t* totals;     // [2]      (N = sum of counts, max count)
+    uint32_t* totals;     // [64]     N, max count, overflow flag, #big tiles, preprocess CTA ticket (see tile_scan.cuh)
+    uint32_t* big_tiles;  // [tiles]  ids of tiles with more than kBigTile pairs
     static size_t required(int W, int H);
     static ImageState carve(void* base, int W, int H);
 };
@@ -89,7 +90,7 @@ size_t sort_temp_bytes(size_t N, int end_bit);
 // raster_preprocess.cu  (compiled with -fmad=false: integer outputs follow the oracle's op order)
 int launch_preprocess(const Camera& cam, int P, const float* means3D, const float* scales, const float* rots,
                       const float* opacities, const float* cov3D_precomp, int32_t* radii, GeomState g,
-                      uint32_t* tile_count, cudaStream_t stream);
+                      ImageState im, uint32_t capacity, cudaStream_t stream);   // also runs the tile scan (last CTA)
 int launch_mark_visible(int P, const float* means3D, const float* view16_host, uint8_t* present, cudaStream_t stream);
 // raster_binning.cu
 int run_scan(GeomState g, int P, cudaStream_t stream);

@@ -7,6 +7,7 @@
 // re-uses the same slabs.  The same pass detects tile boundaries (identifyTileRanges).
 #include <cub/cub.cuh>
 #include "gpsg_internal.cuh"
+#include "tile_scan.cuh"
 
 namespace gpsg {
 
@@ -80,58 +81,14 @@ int run_sort(BinningState b, size_t N, int end_bit, cudaStream_t stream) {
 // most one pair per tile), so point lists, keys and ranges are bit-identical to the radix path and to the oracle.
 // =====================================================================================================
 
-// one CTA: exclusive scan of the per-tile counts -> ranges[t] = (start, end); totals = (N, max count); cursors = 0
-__global__ void __launch_bounds__(1024) tile_scan_kernel(int tiles, ImageState im, uint32_t capacity) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry, smax;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { carry = 0; smax = 0; }
-    __syncthreads();
-    uint32_t local_max = 0;
-    for (int base = 0; base < tiles; base += 1024) {
-        const int t = base + tid;
-        const uint32_t c = t < tiles ? im.tile_count[t] : 0u;
-        local_max = max(local_max, c);
-        uint32_t v = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane >= o) v += u;
-        }
-        if (lane == 31) warp_sums[warp] = v;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warp_sums[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += u;
-            }
-            warp_sums[lane] = w;
-        }
-        __syncthreads();
-        const uint32_t incl = v + (warp ? warp_sums[warp - 1] : 0u) + carry;
-        if (t < tiles) {
-            im.ranges[t] = c ? make_uint2(incl - c, incl) : make_uint2(0u, 0u);   // empty tiles stay (0,0) as upstream
-            im.tile_cursor[t] = 0u;
-        }
-        __syncthreads();
-        if (tid == 1023) carry = incl;
-        __syncthreads();
-    }
-    local_max = __reduce_max_sync(0xffffffffu, local_max);
-    if (lane == 0) atomicMax(&smax, local_max);
-    __syncthreads();
-    if (tid == 0) {
-        im.totals[0] = carry;
-        im.totals[1] = smax;
-        // planned (sync-free) mode: later kernels skip their work if the pairs do not fit / a tile is too long
-        im.totals[2] = (capacity != 0u && (carry > capacity || smax > kMaxTileSort)) ? 1u : 0u;
-    }
+// exclusive scan of the per-tile counts -> ranges[t], totals, big-tile list (tile_scan.cuh).  Normally executed by the
+// last CTA of the preprocess kernel; this standalone launch only serves the P == 0 case.
+__global__ void __launch_bounds__(256) tile_scan_kernel(int tiles, ImageState im, uint32_t capacity) {
+    tile_scan_block(tiles, im, capacity);
 }
 
 int launch_tile_scan(const Camera& cam, ImageState im, uint32_t capacity, cudaStream_t stream) {
-    tile_scan_kernel<<<1, 1024, 0, stream>>>(cam.grid_x * cam.grid_y, im, capacity);
+    tile_scan_kernel<<<1, 256, 0, stream>>>(cam.grid_x * cam.grid_y, im, capacity);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
 }
@@ -141,16 +98,14 @@ int launch_tile_scan(const Camera& cam, ImageState im, uint32_t capacity, cudaSt
 // (CTA, touched tile) for the CTA's base inside the bucket.  Order inside a bucket is irrelevant (sorted next).
 __global__ void __launch_bounds__(256) bucket_scatter_kernel(const __grid_constant__ Camera cam, int P,
                                                              const int32_t* __restrict__ radii, GeomState g,
-                                                             BinningState b, ImageState im, int smem_hist) {
-    extern __shared__ uint32_t sh[];            // [tiles] local counts, then [tiles] CTA bases
+                                                             BinningState b, ImageState im) {
+    __shared__ uint32_t sh_cnt[kBoxBins];       // CTA-local counts over the CTA's tile bounding box ...
+    __shared__ uint32_t sh_base[kBoxBins];      // ... and the CTA's base inside each touched bucket
+    __shared__ int s_bb[4];
     if (im.totals[2]) return;                   // planned mode overflow: nothing may be written
-    const int tiles = cam.grid_x * cam.grid_y;
-    uint32_t* sh_cnt = sh;
-    uint32_t* sh_base = sh + tiles;
-    if (smem_hist) {
-        for (int t = threadIdx.x; t < tiles; t += blockDim.x) sh_cnt[t] = 0u;
-        __syncthreads();
-    }
+    if (threadIdx.x == 0) { s_bb[0] = 0x7fffffff; s_bb[1] = 0x7fffffff; s_bb[2] = 0; s_bb[3] = 0; }
+    for (int t = threadIdx.x; t < kBoxBins; t += blockDim.x) sh_cnt[t] = 0u;
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int rx0 = 0, ry0 = 0, rx1 = 0, ry1 = 0;
     uint2 entry = make_uint2(0u, 0u);
@@ -166,7 +121,8 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(const __grid_consta
             entry = make_uint2((uint32_t)i, __float_as_uint(g.depths[i]));   // little-endian u64 = depth<<32 | id
         }
     }
-    if (!smem_hist) {   // huge tile grids: one global atomic per pair
+    TileBox box;
+    if (!cta_tile_box(rx0, ry0, rx1, ry1, s_bb, box)) {   // splats of this CTA spread too far: one global atomic per pair
         for (int y = ry0; y < ry1; ++y)
             for (int x = rx0; x < rx1; ++x) {
                 const int t = y * cam.grid_x + x;
@@ -175,19 +131,20 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(const __grid_consta
         return;
     }
     for (int y = ry0; y < ry1; ++y)
-        for (int x = rx0; x < rx1; ++x) atomicAdd(&sh_cnt[y * cam.grid_x + x], 1u);
+        for (int x = rx0; x < rx1; ++x) atomicAdd(&sh_cnt[(y - box.y0) * box.w + (x - box.x0)], 1u);
     __syncthreads();
-    for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+    for (int t = threadIdx.x; t < box.w * box.h; t += blockDim.x) {
         const uint32_t c = sh_cnt[t];
         if (c) {
-            sh_base[t] = im.ranges[t].x + atomicAdd(&im.tile_cursor[t], c);
+            const int tile = (box.y0 + t / box.w) * cam.grid_x + box.x0 + t % box.w;
+            sh_base[t] = im.ranges[tile].x + atomicAdd(&im.tile_cursor[tile], c);
             sh_cnt[t] = 0u;
         }
     }
     __syncthreads();
     for (int y = ry0; y < ry1; ++y)
         for (int x = rx0; x < rx1; ++x) {
-            const int t = y * cam.grid_x + x;
+            const int t = (y - box.y0) * box.w + (x - box.x0);
             b.bucket[sh_base[t] + atomicAdd(&sh_cnt[t], 1u)] = entry;
         }
 }
@@ -195,9 +152,7 @@ __global__ void __launch_bounds__(256) bucket_scatter_kernel(const __grid_consta
 int launch_bucket_scatter(const Camera& cam, int P, const int32_t* radii, GeomState g, BinningState b, ImageState im,
                           cudaStream_t stream) {
     if (P <= 0) return GPSG_OK;
-    const size_t bytes = 2 * sizeof(uint32_t) * (size_t)cam.grid_x * cam.grid_y;
-    const int smem_hist = bytes <= 48 * 1024 ? 1 : 0;
-    bucket_scatter_kernel<<<(P + 255) / 256, 256, smem_hist ? bytes : 0, stream>>>(cam, P, radii, g, b, im, smem_hist);
+    bucket_scatter_kernel<<<(P + 255) / 256, 256, 0, stream>>>(cam, P, radii, g, b, im);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
 }
@@ -337,28 +292,37 @@ struct TileSort {
     }
 };
 
-// BIG = false: tiles with n <= 2048 (2/4/8 keys per thread);  BIG = true: only tiles with 2048 < n <= 4096.
-// Two kernels so that the common case is not held at the register / shared-memory footprint of the rare one.
+// BIG = false: one CTA per tile, tiles with n <= 2048 (2/4/8 keys per thread).  BIG = true: a small persistent grid
+// that walks the list of big tiles (2048 < n <= 4096) built by the tile scan -- it costs ~nothing when the list is
+// empty, so the planned (sync-free) path can always launch it.  Two kernels so that the common case is not held at
+// the register / shared-memory footprint of the rare one.
 template <bool BIG>
-__global__ void __launch_bounds__(256) tile_sort_gather_kernel(const float* __restrict__ colors, GeomState g,
-                                                               BinningState b, ImageState im, int id_bits) {
+__global__ void __launch_bounds__(256, BIG ? 1 : 4) tile_sort_gather_kernel(const float* __restrict__ colors, GeomState g,
+                                                                            BinningState b, ImageState im, int id_bits) {
     __shared__ int flags[4];
     if (im.totals[2]) return;                   // planned mode overflow
-    const uint32_t tile = blockIdx.x;
-    const uint2 range = im.ranges[tile];
-    const int n = (int)(range.y - range.x);
-    const unsigned long long* __restrict__ src = reinterpret_cast<const unsigned long long*>(b.bucket) + range.x;
     if constexpr (BIG) {
         __shared__ typename TileSort<16>::Smem t16;
-        if (n <= 2048) return;
-        TileSort<16>::run(t16, flags, src, n, id_bits, tile, range.x, colors, g, b);
+        const uint32_t nbig = im.totals[3];
+        for (uint32_t k = blockIdx.x; k < nbig; k += gridDim.x) {
+            const uint32_t tile = im.big_tiles[k];
+            const uint2 range = im.ranges[tile];
+            const int n = (int)(range.y - range.x);
+            const unsigned long long* __restrict__ src = reinterpret_cast<const unsigned long long*>(b.bucket) + range.x;
+            TileSort<16>::run(t16, flags, src, n, id_bits, tile, range.x, colors, g, b);
+            __syncthreads();
+        }
     } else {
         __shared__ union {
             typename TileSort<2>::Smem t2;
             typename TileSort<4>::Smem t4;
             typename TileSort<8>::Smem t8;
         } temp;
-        if (n == 0 || n > 2048) return;
+        const uint32_t tile = blockIdx.x;
+        const uint2 range = im.ranges[tile];
+        const int n = (int)(range.y - range.x);
+        if (n == 0 || n > (int)kBigTile) return;
+        const unsigned long long* __restrict__ src = reinterpret_cast<const unsigned long long*>(b.bucket) + range.x;
         if (n <= 512) TileSort<2>::run(temp.t2, flags, src, n, id_bits, tile, range.x, colors, g, b);
         else if (n <= 1024) TileSort<4>::run(temp.t4, flags, src, n, id_bits, tile, range.x, colors, g, b);
         else TileSort<8>::run(temp.t8, flags, src, n, id_bits, tile, range.x, colors, g, b);
@@ -369,10 +333,11 @@ int launch_tile_sort_gather(const Camera& cam, int P, uint32_t max_count, const 
                             BinningState b, ImageState im, cudaStream_t stream) {
     int id_bits = 1;
     while (id_bits < 32 && (1ll << id_bits) < (long long)P) ++id_bits;
-    tile_sort_gather_kernel<false><<<cam.grid_x * cam.grid_y, 256, 0, stream>>>(colors, g, b, im, id_bits);
+    const int tiles = cam.grid_x * cam.grid_y;
+    tile_sort_gather_kernel<false><<<tiles, 256, 0, stream>>>(colors, g, b, im, id_bits);
     GPSG_LAUNCH_CHECK();
-    if (max_count > 2048) {
-        tile_sort_gather_kernel<true><<<cam.grid_x * cam.grid_y, 256, 0, stream>>>(colors, g, b, im, id_bits);
+    if (max_count > kBigTile) {   // exact mode passes the real maximum; planned mode passes kMaxTileSort (always launch)
+        tile_sort_gather_kernel<true><<<min(tiles, 148), 256, 0, stream>>>(colors, g, b, im, id_bits);
         GPSG_LAUNCH_CHECK();
     }
     return GPSG_OK;

@@ -6,6 +6,7 @@
 // operation order (documented in DESIGN.md "fp32 op order") and must not be FMA-contracted.
 // It is HBM-bound (56 B in, 40 B out per Gaussian), so the lost FMAs cost nothing.
 #include "gpsg_internal.cuh"
+#include "tile_scan.cuh"
 
 namespace gpsg {
 
@@ -37,16 +38,15 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
                                                          const float* __restrict__ rots,
                                                          const float* __restrict__ opacities,
                                                          const float* __restrict__ cov3D_precomp,
-                                                         int32_t* __restrict__ radii, GeomState g,
-                                                         uint32_t* __restrict__ tile_count, int smem_hist) {
-    // Pairs-per-tile histogram, privatised per CTA in shared memory: the 256 consecutive (pixel-aligned) Gaussians
-    // of a CTA land in a handful of tiles, so ~1.3 M hot global atomics become a few dozen per CTA.
-    extern __shared__ uint32_t sh_cnt[];
-    const int tiles = cam.grid_x * cam.grid_y;
-    if (smem_hist) {
-        for (int t = threadIdx.x; t < tiles; t += blockDim.x) sh_cnt[t] = 0u;
-        __syncthreads();
-    }
+                                                         int32_t* __restrict__ radii, GeomState g, ImageState im,
+                                                         uint32_t capacity) {
+    __shared__ uint32_t sh_cnt[kBoxBins];
+    __shared__ int s_bb[4];
+    __shared__ int s_last;
+    if (threadIdx.x == 0) { s_bb[0] = 0x7fffffff; s_bb[1] = 0x7fffffff; s_bb[2] = 0; s_bb[3] = 0; }
+    for (int t = threadIdx.x; t < kBoxBins; t += blockDim.x) sh_cnt[t] = 0u;
+    __syncthreads();
+    int bx0 = 0, by0 = 0, bx1 = 0, by1 = 0;   // this thread's tile rectangle (empty if culled)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int32_t out_radius = 0;
     uint32_t out_tiles = 0;
@@ -117,32 +117,46 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
         g.conic_opacity[i] = make_float4(conx, cony, conz, opacities[i]);
         out_radius = my_radius;
         out_tiles = (uint32_t)area;
-        if (tile_count)  // tile-bucket binning: pairs per tile (sizes the buckets, replaces the per-Gaussian scan)
-            for (int tile_y = ry0; tile_y < ry1; ++tile_y)
-                for (int tile_x = rx0; tile_x < rx1; ++tile_x)
-                    atomicAdd(smem_hist ? &sh_cnt[tile_y * cam.grid_x + tile_x] : &tile_count[tile_y * cam.grid_x + tile_x], 1u);
+        bx0 = rx0; by0 = ry0; bx1 = rx1; by1 = ry1;
     } while (0);
     if (i < P) {
         radii[i] = out_radius;
         g.tiles_touched[i] = out_tiles;
     }
-    if (smem_hist) {
+    // ---- pairs-per-tile histogram (sizes the tile buckets; replaces upstream's per-Gaussian scan) ----
+    // Privatised per CTA over the bounding box of the CTA's splats: 256 consecutive pixel-aligned Gaussians land in
+    // a handful of tiles, so ~1.3 M hot global atomics become a few per CTA.  Box too large -> direct global atomics.
+    TileBox box;
+    const bool local = cta_tile_box(bx0, by0, bx1, by1, s_bb, box);
+    if (local) {
+        for (int ty = by0; ty < by1; ++ty)
+            for (int tx = bx0; tx < bx1; ++tx) atomicAdd(&sh_cnt[(ty - box.y0) * box.w + (tx - box.x0)], 1u);
         __syncthreads();
-        for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+        for (int t = threadIdx.x; t < box.w * box.h; t += blockDim.x) {
             const uint32_t c = sh_cnt[t];
-            if (c) atomicAdd(&tile_count[t], c);
+            if (c) atomicAdd(&im.tile_count[(box.y0 + t / box.w) * cam.grid_x + box.x0 + t % box.w], c);
         }
+    } else {
+        for (int ty = by0; ty < by1; ++ty)
+            for (int tx = bx0; tx < bx1; ++tx) atomicAdd(&im.tile_count[ty * cam.grid_x + tx], 1u);
+    }
+    // ---- last CTA to finish scans the histogram into tile ranges (no separate launch) ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&im.totals[4], 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        tile_scan_block(cam.grid_x * cam.grid_y, im, capacity);
     }
 }
 
 int launch_preprocess(const Camera& cam, int P, const float* means3D, const float* scales, const float* rots,
                       const float* opacities, const float* cov3D_precomp, int32_t* radii, GeomState g,
-                      uint32_t* tile_count, cudaStream_t stream) {
+                      ImageState im, uint32_t capacity, cudaStream_t stream) {
     if (P <= 0) return GPSG_OK;
-    const size_t hist_bytes = sizeof(uint32_t) * (size_t)cam.grid_x * cam.grid_y;
-    const int smem_hist = (tile_count && hist_bytes <= 48 * 1024) ? 1 : 0;   // larger images: direct global atomics
-    preprocess_kernel<<<(P + 255) / 256, 256, smem_hist ? hist_bytes : 0, stream>>>(
-        cam, P, means3D, scales, rots, opacities, cov3D_precomp, radii, g, tile_count, smem_hist);
+    preprocess_kernel<<<(P + 255) / 256, 256, 0, stream>>>(cam, P, means3D, scales, rots, opacities, cov3D_precomp,
+                                                          radii, g, im, capacity);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
 }

@@ -1,0 +1,79 @@
+// tile_scan.cuh -- block-level exclusive scan of the per-tile pair counts -> tile ranges, totals, big-tile list.
+// Executed by the LAST CTA of the preprocess kernel ("last block done" ticket), so the forward needs no separate
+// scan launch; a thin kernel wrapper exists for the P == 0 case.
+#pragma once
+#include "gpsg_internal.cuh"
+
+namespace gpsg {
+
+// totals[0] = N, [1] = longest tile list, [2] = overflow flag (planned mode), [3] = number of big tiles (> kBigTile)
+constexpr uint32_t kBigTile = 2048;
+
+__device__ __forceinline__ void tile_scan_block(int tiles, const ImageState& im, uint32_t capacity) {
+    __shared__ uint32_t ws[32];
+    __shared__ uint32_t s_max;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = (nthr + 31) >> 5;
+    const int per = (tiles + nthr - 1) / nthr;
+    const int t0 = tid * per, t1 = min(tiles, t0 + per);
+    if (tid == 0) s_max = 0;
+    uint32_t sum = 0, mx = 0;
+    for (int t = t0; t < t1; ++t) {
+        const uint32_t c = __ldcg(&im.tile_count[t]);
+        sum += c;
+        mx = max(mx, c);
+    }
+    uint32_t v = sum;   // inclusive warp scan of the per-thread sums
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    if (lane == 31) ws[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < nwarp ? ws[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += u;
+        }
+        ws[lane] = w;
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0) atomicMax(&s_max, mx);
+    __syncthreads();
+    uint32_t run = v - sum + (warp ? ws[warp - 1] : 0u);   // exclusive prefix of this thread's first tile
+    for (int t = t0; t < t1; ++t) {
+        const uint32_t c = __ldcg(&im.tile_count[t]);
+        im.ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);   // empty tiles stay (0,0) as upstream
+        im.tile_cursor[t] = 0u;
+        if (c > kBigTile) im.big_tiles[atomicAdd(&im.totals[3], 1u)] = (uint32_t)t;
+        run += c;
+    }
+    if (tid == nthr - 1) {
+        const uint32_t total = ws[nwarp - 1];
+        im.totals[0] = total;
+        im.totals[1] = s_max;
+        // planned (sync-free) mode: later kernels skip their work if the pairs do not fit / a tile is too long
+        im.totals[2] = (capacity != 0u && (total > capacity || s_max > kMaxTileSort)) ? 1u : 0u;
+    }
+}
+
+// CTA-local histogram over the bounding box (in tiles) of the CTA's splats.  Returns true if the box fits.
+struct TileBox { int x0, y0, w, h; };
+constexpr int kBoxBins = 1024;
+
+__device__ __forceinline__ bool cta_tile_box(int rx0, int ry0, int rx1, int ry1, int* s_bb, TileBox& box) {
+    // s_bb: 4 shared ints, must have been initialised to {INT_MAX, INT_MAX, 0, 0} and synchronised
+    const bool has = rx1 > rx0 && ry1 > ry0;
+    int a = has ? rx0 : 0x7fffffff, b = has ? ry0 : 0x7fffffff, c = has ? rx1 : 0, d = has ? ry1 : 0;
+    a = __reduce_min_sync(0xffffffffu, a); b = __reduce_min_sync(0xffffffffu, b);
+    c = __reduce_max_sync(0xffffffffu, c); d = __reduce_max_sync(0xffffffffu, d);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&s_bb[0], a); atomicMin(&s_bb[1], b); atomicMax(&s_bb[2], c); atomicMax(&s_bb[3], d); }
+    __syncthreads();
+    box.x0 = s_bb[0]; box.y0 = s_bb[1];
+    box.w = max(0, s_bb[2] - s_bb[0]); box.h = max(0, s_bb[3] - s_bb[1]);
+    return box.w * box.h <= kBoxBins;
+}
+
+}  // namespace gpsg
