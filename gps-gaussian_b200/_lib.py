@@ -80,6 +80,15 @@ lib.gpsg_raster_status_ptr.restype = _vp
 lib.gpsg_raster_status_ptr.argtypes = [_vp, _i, _i]
 lib.gpsg_rasterize_forward_planned.restype = _i
 lib.gpsg_rasterize_forward_planned.argtypes = [C.POINTER(RasterSettings), _i, _vp, _i] + [_vp] * 10 + [_i64, _vp, _vp]
+_pp = C.POINTER(C.c_void_p)
+lib.gpsg_rasterize_forward_maps.restype = _i
+lib.gpsg_rasterize_forward_maps.argtypes = [C.POINTER(RasterSettings), _i, _vp, _i, _pp, _pp, _pp, _pp, _pp, _pp, _vp, _vp,
+                                            ALLOC_FN, _vp, ALLOC_FN, _vp, ALLOC_FN, _vp, C.POINTER(C.c_int32)]
+lib.gpsg_rasterize_backward_maps_workspace_bytes.restype = _sz
+lib.gpsg_rasterize_backward_maps_workspace_bytes.argtypes = [_i]
+lib.gpsg_rasterize_backward_maps.restype = _i
+lib.gpsg_rasterize_backward_maps.argtypes = [C.POINTER(RasterSettings), _i, _vp, _i, C.c_int32, _pp, _pp, _pp, _pp, _pp, _pp,
+                                             _vp, _vp, _vp, _vp, _vp, _pp, _pp, _pp, _pp, _pp, _vp]
 lib.gpsg_corr_build_pyramid.restype = _i
 lib.gpsg_corr_build_pyramid.argtypes = [_i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, C.POINTER(C.c_void_p), _i]
 lib.gpsg_corr_lookup_pyramid_forward.restype = _i
@@ -100,7 +109,8 @@ EXPORTED = ["gpsg_last_error", "gpsg_version", "gpsg_rasterize_forward", "gpsg_r
             "gpsg_corr_sampler_forward", "gpsg_corr_sampler_backward", "gpsg_corr_build_pyramid",
             "gpsg_corr_lookup_pyramid_forward", "gpsg_corr_lookup_pyramid_backward", "gpsg_raster_geom_bytes",
             "gpsg_raster_binning_bytes", "gpsg_raster_image_bytes", "gpsg_raster_status_ptr",
-            "gpsg_rasterize_forward_planned", "gpsg_profile_enable", "gpsg_profile_read",
+            "gpsg_rasterize_forward_planned", "gpsg_rasterize_forward_maps", "gpsg_rasterize_backward_maps_workspace_bytes",
+            "gpsg_rasterize_backward_maps", "gpsg_profile_enable", "gpsg_profile_read",
             "gpsg_profile_stage_name"]
 
 

@@ -114,6 +114,16 @@ size_t ImageState::required(int W, int H) {
 }
 ImageState ImageState::carve(void* base, int W, int H) { return carve_image((char*)align_up((size_t)base), W, H, nullptr); }
 
+
+static GaussianSrc aos_src(const float* means3D, const float* scales, const float* rots, const float* opacities,
+                           const float* colors, const float* cov3D_precomp) {
+    GaussianSrc src;
+    memset(&src, 0, sizeof(src));
+    src.means3D = means3D; src.scales = scales; src.rots = rots; src.opacities = opacities; src.colors = colors;
+    src.cov3D_precomp = cov3D_precomp;
+    return src;
+}
+
 static int bit_length(uint32_t n) {
     int b = 0;
     while (n) { ++b; n >>= 1; }
@@ -177,6 +187,79 @@ extern "C" {
 GPSG_API const char* gpsg_last_error(void) { return g_err; }
 int gpsg_version(void) { return 100; }
 
+// Shared body of the exact (one host read) forward: `src` says where the Gaussians come from (AoS tensors or maps).
+static int forward_exact(const GpsgRasterSettings* s, int device, cudaStream_t stream, int P, int sh_M, GaussianSrc src,
+                         const float* shs, float* out_color, int32_t* radii, gpsg_alloc_fn geom_alloc, void* geom_user,
+                         gpsg_alloc_fn binning_alloc, void* binning_user, gpsg_alloc_fn image_alloc, void* image_user,
+                         int32_t* num_rendered) {
+    GPSG_CUDA(cudaSetDevice(device));
+    const Camera cam = make_camera(*s);
+
+    const size_t scan_bytes = scan_temp_bytes(P);
+    void* geom_base = geom_alloc(geom_user, GeomState::required(P, scan_bytes));
+    if (!geom_base) { set_error("geometry allocator returned NULL"); return GPSG_E_ALLOC; }
+    GeomState g = GeomState::carve(geom_base, P, scan_bytes);
+    void* img_base = image_alloc(image_user, ImageState::required(cam.W, cam.H));
+    if (!img_base) { set_error("image allocator returned NULL"); return GPSG_E_ALLOC; }
+    ImageState im = ImageState::carve(img_base, cam.W, cam.H);
+    const int tiles = cam.grid_x * cam.grid_y;
+
+    // ---- per-Gaussian projection + pairs-per-tile counts, then tile ranges; one host read: (N, max tile count)
+    uint32_t N = 0, max_count = 0;
+    int rc = GPSG_OK;
+    GPSG_CUDA(cudaMemsetAsync(im.tile_count, 0, (size_t)((char*)(im.totals + 64) - (char*)im.tile_count), stream));
+    if (P > 0) {   // projection + pairs-per-tile histogram; its last CTA also scans the histogram into tile ranges
+        { StageTimer t(ST_PREPROCESS, stream, 1); rc = launch_preprocess(cam, P, src, radii, g, im, 0u, stream); }
+        if (rc) return rc;
+    } else {
+        { StageTimer t(ST_TILE_SCAN, stream, 1); rc = launch_tile_scan(cam, im, 0u, stream); }
+        if (rc) return rc;
+    }
+    if (P > 0) {
+        uint32_t* slot = pinned_slot();
+        GPSG_REQUIRE(slot != nullptr, "cudaHostAlloc failed");
+        GPSG_CUDA(cudaMemcpyAsync(slot, im.totals, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        GPSG_CUDA(cudaStreamSynchronize(stream));
+        N = slot[0];
+        max_count = slot[1];
+    }
+    if (num_rendered) *num_rendered = (int32_t)N;
+    if (shs && P > 0) {   // SH -> RGB for the visible Gaussians (kept in the geometry buffer for the backward)
+        rc = launch_sh_forward(P, s->sh_degree, sh_M, s->campos, src.means3D, shs, radii, g.rgb, g.clamped, stream);
+        if (rc) return rc;
+        src.colors = g.rgb;
+    }
+
+    const bool radix_path = max_count > kMaxTileSort || force_radix_binning();
+    const int end_bit = 32 + bit_length((uint32_t)tiles);
+    const size_t sort_bytes = radix_path ? sort_temp_bytes(N, end_bit) : 0;
+    void* bin_base = binning_alloc(binning_user, BinningState::required(N, sort_bytes));
+    if (!bin_base) { set_error("binning allocator returned NULL"); return GPSG_E_ALLOC; }
+    BinningState b = BinningState::carve(bin_base, N, sort_bytes);
+
+    if (N > 0 && !radix_path) {
+        // tile-bucket binning: scatter into per-tile buckets, sort each tile inside one CTA, gather slabs
+        { StageTimer t(ST_SCATTER, stream, 1); rc = launch_bucket_scatter(cam, P, radii, g, b, im, stream); }
+        if (rc) return rc;
+        { StageTimer t(ST_TILE_SORT, stream, max_count > 2048 ? 2 : 1); rc = launch_tile_sort_gather(cam, P, max_count, src, g, b, im, stream); }
+        if (rc) return rc;
+    } else if (N > 0) {
+        // fallback (a tile list too long for the in-CTA sort, or GPSG_BINNING=radix): upstream-style global radix sort
+        { StageTimer t(ST_SCAN, stream, 2); rc = run_scan(g, P, stream); }
+        if (rc) return rc;
+        { StageTimer t(ST_DUPLICATE, stream, 1); rc = launch_duplicate(cam, P, radii, g, b, stream); }
+        if (rc) return rc;
+        { StageTimer t(ST_SORT, stream, 2 + (end_bit + 7) / 8); rc = run_sort(b, N, end_bit, stream); }
+        if (rc) return rc;
+        { StageTimer t(ST_GATHER, stream, 1); rc = launch_gather_ranges(cam, N, src, g, b, im, stream); }
+        if (rc) return rc;
+    }
+    { StageTimer t(ST_RENDER_FWD, stream, 1); rc = launch_render_forward(cam, b, im, out_color, stream); }
+    if (rc) return rc;
+    if (s->debug) GPSG_CUDA(cudaStreamSynchronize(stream));
+    return GPSG_OK;
+}
+
 int gpsg_rasterize_forward(const GpsgRasterSettings* s, int device, void* stream_, int P, int sh_M,
                            const float* means3D, const float* colors_precomp, const float* shs,
                            const float* opacities, const float* scales, const float* rotations,
@@ -199,73 +282,48 @@ int gpsg_rasterize_forward(const GpsgRasterSettings* s, int device, void* stream
             GPSG_REQUIRE(sh_M >= (s->sh_degree + 1) * (s->sh_degree + 1), "shs has fewer coefficients than (sh_degree+1)^2");
         }
     }
-    cudaStream_t stream = (cudaStream_t)stream_;
-    GPSG_CUDA(cudaSetDevice(device));
-    const Camera cam = make_camera(*s);
+    return forward_exact(s, device, (cudaStream_t)stream_, P, sh_M,
+                         aos_src(means3D, cov3D_precomp ? nullptr : scales, cov3D_precomp ? nullptr : rotations, opacities,
+                                 colors_precomp, cov3D_precomp),
+                         shs, out_color, radii, geom_alloc, geom_user, binning_alloc, binning_user, image_alloc, image_user,
+                         num_rendered);
+}
 
-    const size_t scan_bytes = scan_temp_bytes(P);
-    void* geom_base = geom_alloc(geom_user, GeomState::required(P, scan_bytes));
-    if (!geom_base) { set_error("geometry allocator returned NULL"); return GPSG_E_ALLOC; }
-    GeomState g = GeomState::carve(geom_base, P, scan_bytes);
-    void* img_base = image_alloc(image_user, ImageState::required(cam.W, cam.H));
-    if (!img_base) { set_error("image allocator returned NULL"); return GPSG_E_ALLOC; }
-    ImageState im = ImageState::carve(img_base, cam.W, cam.H);
-    const int tiles = cam.grid_x * cam.grid_y;
-
-    // ---- per-Gaussian projection + pairs-per-tile counts, then tile ranges; one host read: (N, max tile count)
-    uint32_t N = 0, max_count = 0;
-    int rc = GPSG_OK;
-    GPSG_CUDA(cudaMemsetAsync(im.tile_count, 0, (size_t)((char*)(im.totals + 64) - (char*)im.tile_count), stream));
-    if (P > 0) {   // projection + pairs-per-tile histogram; its last CTA also scans the histogram into tile ranges
-        { StageTimer t(ST_PREPROCESS, stream, 1); rc = launch_preprocess(cam, P, means3D, scales, rotations, opacities, cov3D_precomp, radii, g, im, 0u, stream); }
-        if (rc) return rc;
-    } else {
-        { StageTimer t(ST_TILE_SCAN, stream, 1); rc = launch_tile_scan(cam, im, 0u, stream); }
-        if (rc) return rc;
-    }
-    if (P > 0) {
-        uint32_t* slot = pinned_slot();
-        GPSG_REQUIRE(slot != nullptr, "cudaHostAlloc failed");
-        GPSG_CUDA(cudaMemcpyAsync(slot, im.totals, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-        GPSG_CUDA(cudaStreamSynchronize(stream));
-        N = slot[0];
-        max_count = slot[1];
-    }
-    if (num_rendered) *num_rendered = (int32_t)N;
-    if (shs && P > 0) {   // SH -> RGB for the visible Gaussians (kept in the geometry buffer for the backward)
-        rc = launch_sh_forward(P, s->sh_degree, sh_M, s->campos, means3D, shs, radii, g.rgb, g.clamped, stream);
-        if (rc) return rc;
-        colors_precomp = g.rgb;
-    }
-
-    const bool radix_path = max_count > kMaxTileSort || force_radix_binning();
-    const int end_bit = 32 + bit_length((uint32_t)tiles);
-    const size_t sort_bytes = radix_path ? sort_temp_bytes(N, end_bit) : 0;
-    void* bin_base = binning_alloc(binning_user, BinningState::required(N, sort_bytes));
-    if (!bin_base) { set_error("binning allocator returned NULL"); return GPSG_E_ALLOC; }
-    BinningState b = BinningState::carve(bin_base, N, sort_bytes);
-
-    if (N > 0 && !radix_path) {
-        // tile-bucket binning: scatter into per-tile buckets, sort each tile inside one CTA, gather slabs
-        { StageTimer t(ST_SCATTER, stream, 1); rc = launch_bucket_scatter(cam, P, radii, g, b, im, stream); }
-        if (rc) return rc;
-        { StageTimer t(ST_TILE_SORT, stream, max_count > 2048 ? 2 : 1); rc = launch_tile_sort_gather(cam, P, max_count, colors_precomp, g, b, im, stream); }
-        if (rc) return rc;
-    } else if (N > 0) {
-        // fallback (a tile list too long for the in-CTA sort, or GPSG_BINNING=radix): upstream-style global radix sort
-        { StageTimer t(ST_SCAN, stream, 2); rc = run_scan(g, P, stream); }
-        if (rc) return rc;
-        { StageTimer t(ST_DUPLICATE, stream, 1); rc = launch_duplicate(cam, P, radii, g, b, stream); }
-        if (rc) return rc;
-        { StageTimer t(ST_SORT, stream, 2 + (end_bit + 7) / 8); rc = run_sort(b, N, end_bit, stream); }
-        if (rc) return rc;
-        { StageTimer t(ST_GATHER, stream, 1); rc = launch_gather_ranges(cam, N, colors_precomp, g, b, im, stream); }
-        if (rc) return rc;
-    }
-    { StageTimer t(ST_RENDER_FWD, stream, 1); rc = launch_render_forward(cam, b, im, out_color, stream); }
-    if (rc) return rc;
-    if (s->debug) GPSG_CUDA(cudaStreamSynchronize(stream));
+static int check_maps(int S2, const uint8_t* const* valid, const float* const* xyz, const float* const* img,
+                      const float* const* rot, const float* const* scale, const float* const* opacity) {
+    GPSG_REQUIRE(S2 > 0 && S2 < (1 << 30), "pixels per view must be positive");
+    GPSG_REQUIRE(valid && xyz && img && rot && scale && opacity, "map pointer array is NULL");
+    for (int v = 0; v < 2; ++v)
+        GPSG_REQUIRE(valid[v] && xyz[v] && img[v] && rot[v] && scale[v] && opacity[v], "a source-view map is NULL");
     return GPSG_OK;
+}
+static GaussianSrc maps_src(int S2, const uint8_t* const* valid, const float* const* xyz, const float* const* img,
+                            const float* const* rot, const float* const* scale, const float* const* opacity) {
+    GaussianSrc src;
+    memset(&src, 0, sizeof(src));
+    src.S2 = S2;
+    for (int v = 0; v < 2; ++v) {
+        src.valid[v] = valid[v]; src.xyz[v] = xyz[v]; src.img[v] = img[v]; src.rot[v] = rot[v]; src.scale[v] = scale[v];
+        src.opac[v] = opacity[v];
+    }
+    return src;
+}
+
+int gpsg_rasterize_forward_maps(const GpsgRasterSettings* s, int device, void* stream_, int pixels_per_view,
+                                const uint8_t* const* valid, const float* const* xyz, const float* const* img,
+                                const float* const* rot, const float* const* scale, const float* const* opacity,
+                                float* out_color, int32_t* radii, gpsg_alloc_fn geom_alloc, void* geom_user,
+                                gpsg_alloc_fn binning_alloc, void* binning_user, gpsg_alloc_fn image_alloc,
+                                void* image_user, int32_t* num_rendered) {
+    GPSG_REQUIRE(s != nullptr, "settings is NULL");
+    GPSG_REQUIRE(s->image_width > 0 && s->image_height > 0, "image size must be positive");
+    GPSG_REQUIRE(out_color && radii, "out_color / radii is NULL");
+    GPSG_REQUIRE(geom_alloc && binning_alloc && image_alloc, "allocator callback is NULL");
+    int rc = check_maps(pixels_per_view, valid, xyz, img, rot, scale, opacity);
+    if (rc) return rc;
+    return forward_exact(s, device, (cudaStream_t)stream_, 2 * pixels_per_view, 0,
+                         maps_src(pixels_per_view, valid, xyz, img, rot, scale, opacity), nullptr, out_color, radii,
+                         geom_alloc, geom_user, binning_alloc, binning_user, image_alloc, image_user, num_rendered);
 }
 
 size_t gpsg_raster_geom_bytes(int P) { return GeomState::required(P > 0 ? P : 0, scan_temp_bytes(P > 0 ? P : 0)); }
@@ -295,14 +353,16 @@ int gpsg_rasterize_forward_planned(const GpsgRasterSettings* s, int device, void
     GeomState g = GeomState::carve(geom_buffer, P, 0);
     ImageState im = ImageState::carve(image_buffer, cam.W, cam.H);
     BinningState b = BinningState::carve(binning_buffer, (size_t)capacity_pairs, 0);
+    const GaussianSrc src = aos_src(means3D, cov3D_precomp ? nullptr : scales, cov3D_precomp ? nullptr : rotations, opacities,
+                                    colors_precomp, cov3D_precomp);
     int rc = GPSG_OK;
     GPSG_CUDA(cudaMemsetAsync(im.tile_count, 0, (size_t)((char*)(im.totals + 64) - (char*)im.tile_count), stream));
-    { StageTimer t(ST_PREPROCESS, stream, 1); rc = launch_preprocess(cam, P, means3D, scales, rotations, opacities, cov3D_precomp, radii, g, im, (uint32_t)capacity_pairs, stream); }
+    { StageTimer t(ST_PREPROCESS, stream, 1); rc = launch_preprocess(cam, P, src, radii, g, im, (uint32_t)capacity_pairs, stream); }
     if (rc) return rc;
     if (status_host) GPSG_CUDA(cudaMemcpyAsync(status_host, im.totals, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     { StageTimer t(ST_SCATTER, stream, 1); rc = launch_bucket_scatter(cam, P, radii, g, b, im, stream); }
     if (rc) return rc;
-    { StageTimer t(ST_TILE_SORT, stream, 2); rc = launch_tile_sort_gather(cam, P, kMaxTileSort, colors_precomp, g, b, im, stream); }
+    { StageTimer t(ST_TILE_SORT, stream, 2); rc = launch_tile_sort_gather(cam, P, kMaxTileSort, src, g, b, im, stream); }
     if (rc) return rc;
     { StageTimer t(ST_RENDER_FWD, stream, 1); rc = launch_render_forward(cam, b, im, out_color, stream); }
     return rc;
@@ -311,6 +371,38 @@ int gpsg_rasterize_forward_planned(const GpsgRasterSettings* s, int device, void
 size_t gpsg_rasterize_backward_workspace_bytes(int P) {
     const size_t n = (size_t)(P > 0 ? P : 1);
     return align_up(sizeof(float4) * n) + align_up(sizeof(float) * 3 * n) + 256;   // dL_dconic+opacity, dL_dcolors (SH path)
+}
+
+static int backward_common(const GpsgRasterSettings* s, int device, cudaStream_t stream, int P, int sh_M,
+                           int32_t num_rendered, const GaussianSrc& src, const float* shs, const int32_t* radii,
+                           const void* geom_buffer, const void* binning_buffer, const void* image_buffer,
+                           const float* dL_dout_color, float* dL_dmeans2D, float* dL_dcolors, float* dL_dsh,
+                           const GaussianGrads& out, void* workspace) {
+    GPSG_CUDA(cudaSetDevice(device));
+    const Camera cam = make_camera(*s);
+    BinningState b = BinningState::carve(const_cast<void*>(binning_buffer), (size_t)num_rendered, 0);
+    ImageState im = ImageState::carve(const_cast<void*>(image_buffer), cam.W, cam.H);
+    GeomState gst = GeomState::carve(const_cast<void*>(geom_buffer), P, 0);
+    float4* dconic_op = (float4*)align_up((size_t)workspace);
+    if (!dL_dcolors) dL_dcolors = (float*)((char*)dconic_op + align_up(sizeof(float4) * (size_t)P));   // scratch
+    GPSG_CUDA(cudaMemsetAsync(dL_dmeans2D, 0, sizeof(float) * 3 * (size_t)P, stream));
+    GPSG_CUDA(cudaMemsetAsync(dL_dcolors, 0, sizeof(float) * 3 * (size_t)P, stream));
+    GPSG_CUDA(cudaMemsetAsync(dconic_op, 0, sizeof(float4) * (size_t)P, stream));
+    int rc = GPSG_OK;
+    if (num_rendered > 0) {
+        { StageTimer t(ST_RENDER_BWD, stream, 1); rc = launch_render_backward(cam, b, im, dL_dout_color, dL_dmeans2D, dconic_op, dL_dcolors, stream); }
+        if (rc) return rc;
+    }
+    { StageTimer t(ST_PREPROCESS_BWD, stream, 1);
+      rc = launch_preprocess_backward(cam, P, src, radii, gst.conic_opacity, dL_dmeans2D, dconic_op, dL_dcolors, out, stream); }
+    if (rc) return rc;
+    if (shs) {
+        rc = launch_sh_backward(P, s->sh_degree, sh_M, s->campos, src.means3D, shs, radii, gst.clamped, dL_dcolors, dL_dsh,
+                                out.dmeans3D, stream);
+        if (rc) return rc;
+    }
+    if (s->debug) GPSG_CUDA(cudaStreamSynchronize(stream));
+    return GPSG_OK;
 }
 
 int gpsg_rasterize_backward(const GpsgRasterSettings* s, int device, void* stream_, int P, int sh_M,
@@ -330,42 +422,57 @@ int gpsg_rasterize_backward(const GpsgRasterSettings* s, int device, void* strea
     GPSG_REQUIRE((shs != nullptr) == (dL_dsh != nullptr), "dL_dsh must be given exactly when shs is");
     GPSG_REQUIRE(shs != nullptr || dL_dcolors != nullptr, "dL_dcolors is NULL");
     GPSG_REQUIRE((scales && rotations) || cov3D_precomp, "need scales+rotations or cov3D_precomp");
-    (void)colors_precomp; (void)opacities;
     cudaStream_t stream = (cudaStream_t)stream_;
-    GPSG_CUDA(cudaSetDevice(device));
-    const Camera cam = make_camera(*s);
-    BinningState b = BinningState::carve(const_cast<void*>(binning_buffer), (size_t)num_rendered, 0);
-    ImageState im = ImageState::carve(const_cast<void*>(image_buffer), cam.W, cam.H);
-    float4* dconic_op = (float4*)align_up((size_t)workspace);
-    if (!dL_dcolors) dL_dcolors = (float*)((char*)dconic_op + align_up(sizeof(float4) * (size_t)P));   // SH path scratch
-    GPSG_CUDA(cudaMemsetAsync(dL_dmeans2D, 0, sizeof(float) * 3 * (size_t)P, stream));
-    GPSG_CUDA(cudaMemsetAsync(dL_dcolors, 0, sizeof(float) * 3 * (size_t)P, stream));
-    GPSG_CUDA(cudaMemsetAsync(dconic_op, 0, sizeof(float4) * (size_t)P, stream));
-    int rc = GPSG_OK;
-    if (num_rendered > 0) {
-        { StageTimer t(ST_RENDER_BWD, stream, 1); rc = launch_render_backward(cam, b, im, dL_dout_color, dL_dmeans2D, dconic_op, dL_dcolors, stream); }
-        if (rc) return rc;
-    }
-    { StageTimer t(ST_PREPROCESS_BWD, stream, 1);
-    GeomState gst = GeomState::carve(const_cast<void*>(geom_buffer), P, 0);
-    rc = launch_preprocess_backward(cam, P, means3D, radii, cov3D_precomp ? nullptr : scales,
-                                    cov3D_precomp ? nullptr : rotations, cov3D_precomp, gst.conic_opacity, dL_dmeans2D,
-                                    dconic_op,
-                                    dL_dopacity, dL_dmeans3D, dL_dcov3D, cov3D_precomp ? nullptr : dL_dscales,
-                                    cov3D_precomp ? nullptr : dL_drotations, stream); }
+    GaussianGrads out;
+    memset(&out, 0, sizeof(out));
+    out.dmeans3D = dL_dmeans3D; out.dopacity = dL_dopacity; out.dcov3D = dL_dcov3D;
+    out.dscales = cov3D_precomp ? nullptr : dL_dscales;
+    out.drots = cov3D_precomp ? nullptr : dL_drotations;
+    int rc = backward_common(s, device, stream, P, sh_M, num_rendered,
+                             aos_src(means3D, cov3D_precomp ? nullptr : scales, cov3D_precomp ? nullptr : rotations,
+                                     opacities, colors_precomp, cov3D_precomp),
+                             shs, radii, geom_buffer, binning_buffer, image_buffer, dL_dout_color, dL_dmeans2D, dL_dcolors,
+                             dL_dsh, out, workspace);
     if (rc) return rc;
-    if (shs) {
-        GeomState g = GeomState::carve(const_cast<void*>(geom_buffer), P, 0);
-        rc = launch_sh_backward(P, s->sh_degree, sh_M, s->campos, means3D, shs, radii, g.clamped, dL_dcolors, dL_dsh,
-                                dL_dmeans3D, stream);
-        if (rc) return rc;
-    }
     if (cov3D_precomp) {
         if (dL_dscales) GPSG_CUDA(cudaMemsetAsync(dL_dscales, 0, sizeof(float) * 3 * (size_t)P, stream));
         if (dL_drotations) GPSG_CUDA(cudaMemsetAsync(dL_drotations, 0, sizeof(float) * 4 * (size_t)P, stream));
     }
-    if (s->debug) GPSG_CUDA(cudaStreamSynchronize(stream));
     return GPSG_OK;
+}
+
+size_t gpsg_rasterize_backward_maps_workspace_bytes(int pixels_per_view) {
+    const size_t n = (size_t)(pixels_per_view > 0 ? 2 * pixels_per_view : 1);
+    return align_up(sizeof(float4) * n) + align_up(sizeof(float) * 3 * n) + align_up(sizeof(float) * 3 * n) + 512;
+}
+
+int gpsg_rasterize_backward_maps(const GpsgRasterSettings* s, int device, void* stream_, int pixels_per_view,
+                                 int32_t num_rendered, const uint8_t* const* valid, const float* const* xyz,
+                                 const float* const* img, const float* const* rot, const float* const* scale,
+                                 const float* const* opacity, const int32_t* radii, const void* geom_buffer,
+                                 const void* binning_buffer, const void* image_buffer, const float* dL_dout_color,
+                                 float* const* dL_dxyz, float* const* dL_dimg, float* const* dL_drot,
+                                 float* const* dL_dscale, float* const* dL_dopacity, void* workspace) {
+    GPSG_REQUIRE(s != nullptr, "settings is NULL");
+    int rc = check_maps(pixels_per_view, valid, xyz, img, rot, scale, opacity);
+    if (rc) return rc;
+    GPSG_REQUIRE(num_rendered >= 0 && radii && geom_buffer && binning_buffer && image_buffer && dL_dout_color && workspace,
+                 "a required input pointer is NULL");
+    GPSG_REQUIRE(dL_dxyz && dL_dimg && dL_drot && dL_dscale && dL_dopacity, "gradient pointer array is NULL");
+    GaussianGrads out;
+    memset(&out, 0, sizeof(out));
+    for (int v = 0; v < 2; ++v) {
+        GPSG_REQUIRE(dL_dxyz[v] && dL_dimg[v] && dL_drot[v] && dL_dscale[v] && dL_dopacity[v], "a gradient map is NULL");
+        out.dxyz[v] = dL_dxyz[v]; out.dimg[v] = dL_dimg[v]; out.drot[v] = dL_drot[v]; out.dscale[v] = dL_dscale[v];
+        out.dopac[v] = dL_dopacity[v];
+    }
+    const int P = 2 * pixels_per_view;
+    // workspace: [float4 P moments][float 3P dL_dcolors][float 3P dL_dmeans2D]
+    char* w = (char*)align_up((size_t)workspace);
+    float* dmeans2D = (float*)(w + align_up(sizeof(float4) * (size_t)P) + align_up(sizeof(float) * 3 * (size_t)P));
+    return backward_common(s, device, (cudaStream_t)stream_, P, 0, num_rendered,
+                           maps_src(pixels_per_view, valid, xyz, img, rot, scale, opacity), nullptr, radii, geom_buffer,
+                           binning_buffer, image_buffer, dL_dout_color, dmeans2D, nullptr, nullptr, out, workspace);
 }
 
 int gpsg_mark_visible(int device, void* stream_, int P, const float* means3D, const float* viewmatrix_host16,

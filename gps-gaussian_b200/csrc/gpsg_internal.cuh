@@ -42,6 +42,55 @@ struct Camera {
 };
 Camera make_camera(const GpsgRasterSettings& s);
 
+
+// ---- where the per-Gaussian inputs / gradients live -------------------------------------------------------------
+// AoS mode: the gathered [P,k] tensors the reference passes to GaussianRasterizer (gaussian_renderer/__init__.py:54-62).
+// Map mode (S2 > 0): the fused ingest of lib/GaussianRender.py:14-33 -- two pixel-aligned source views with S2 pixels
+// each, read in place (xyz[S2,3] AoS, CHW planes for img/rot/scale/opacity, a validity mask); Gaussian i = view*S2 +
+// pixel, invalid pixels are culled in-kernel, colours are img*0.5+0.5.  Same relative order as the reference's
+// boolean-mask gather + concat, so results are identical.
+struct GaussianSrc {
+    const float* means3D; const float* scales; const float* rots; const float* opacities; const float* colors;
+    const float* cov3D_precomp;
+    int S2;
+    const uint8_t* valid[2]; const float* xyz[2]; const float* img[2]; const float* rot[2]; const float* scale[2];
+    const float* opac[2];
+};
+struct GaussianGrads {
+    float* dmeans3D; float* dscales; float* drots; float* dopacity; float* dcov3D;         // AoS mode
+    float* dxyz[2]; float* dimg[2]; float* drot[2]; float* dscale[2]; float* dopac[2];     // map mode
+};
+#ifdef __CUDACC__
+// geometry of Gaussian i; false = not a Gaussian (invalid pixel)
+__device__ __forceinline__ bool src_geom(const GaussianSrc& s, int i, float& x, float& y, float& z, float sc[3], float4& q,
+                                         float& op) {
+    if (s.S2 == 0) {
+        x = s.means3D[3 * i]; y = s.means3D[3 * i + 1]; z = s.means3D[3 * i + 2];
+        if (!s.cov3D_precomp) {
+            sc[0] = s.scales[3 * i]; sc[1] = s.scales[3 * i + 1]; sc[2] = s.scales[3 * i + 2];
+            q = make_float4(s.rots[4 * i], s.rots[4 * i + 1], s.rots[4 * i + 2], s.rots[4 * i + 3]);
+        }
+        op = s.opacities[i];
+        return true;
+    }
+    const int v = i >= s.S2 ? 1 : 0, px = i - v * s.S2;
+    if (!s.valid[v][px]) return false;
+    const float* xyz = s.xyz[v] + 3 * (size_t)px;
+    x = xyz[0]; y = xyz[1]; z = xyz[2];
+    const size_t S2 = (size_t)s.S2;
+    sc[0] = s.scale[v][px]; sc[1] = s.scale[v][S2 + px]; sc[2] = s.scale[v][2 * S2 + px];
+    q = make_float4(s.rot[v][px], s.rot[v][S2 + px], s.rot[v][2 * S2 + px], s.rot[v][3 * S2 + px]);
+    op = s.opac[v][px];
+    return true;
+}
+__device__ __forceinline__ void src_color(const GaussianSrc& s, uint32_t id, float& r, float& g, float& b) {
+    if (s.S2 == 0) { r = s.colors[3 * id]; g = s.colors[3 * id + 1]; b = s.colors[3 * id + 2]; return; }
+    const int v = (int)id >= s.S2 ? 1 : 0;
+    const size_t px = id - (uint32_t)(v * s.S2), S2 = (size_t)s.S2;
+    r = s.img[v][px] * 0.5f + 0.5f; g = s.img[v][S2 + px] * 0.5f + 0.5f; b = s.img[v][2 * S2 + px] * 0.5f + 0.5f;
+}
+#endif
+
 static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 // ---- saved-state layouts (carved from the caller-allocated byte buffers) -------------------
@@ -88,22 +137,21 @@ size_t sort_temp_bytes(size_t N, int end_bit);
 
 // ---- kernel launchers (each enqueues on `stream`) ------------------------------------------
 // raster_preprocess.cu  (compiled with -fmad=false: integer outputs follow the oracle's op order)
-int launch_preprocess(const Camera& cam, int P, const float* means3D, const float* scales, const float* rots,
-                      const float* opacities, const float* cov3D_precomp, int32_t* radii, GeomState g,
-                      ImageState im, uint32_t capacity, cudaStream_t stream);   // also runs the tile scan (last CTA)
+int launch_preprocess(const Camera& cam, int P, const GaussianSrc& src, int32_t* radii, GeomState g, ImageState im,
+                      uint32_t capacity, cudaStream_t stream);   // also runs the tile scan (last CTA)
 int launch_mark_visible(int P, const float* means3D, const float* view16_host, uint8_t* present, cudaStream_t stream);
 // raster_binning.cu
 int run_scan(GeomState g, int P, cudaStream_t stream);
 int launch_duplicate(const Camera& cam, int P, const int32_t* radii, GeomState g, BinningState b, cudaStream_t stream);
 int run_sort(BinningState b, size_t N, int end_bit, cudaStream_t stream);
-int launch_gather_ranges(const Camera& cam, size_t N, const float* colors, GeomState g, BinningState b, ImageState im,
+int launch_gather_ranges(const Camera& cam, size_t N, const GaussianSrc& src, GeomState g, BinningState b, ImageState im,
                          cudaStream_t stream);
 // tile-bucket path (default): counts -> ranges, bucket scatter, per-tile in-CTA sort fused with the slab gather
 constexpr uint32_t kMaxTileSort = 4096;  // largest tile list the in-CTA sort handles (256 thr x 16 keys); beyond: radix path
 int launch_tile_scan(const Camera& cam, ImageState im, uint32_t capacity /*0 = unbounded*/, cudaStream_t stream);
 int launch_bucket_scatter(const Camera& cam, int P, const int32_t* radii, GeomState g, BinningState b, ImageState im,
                           cudaStream_t stream);
-int launch_tile_sort_gather(const Camera& cam, int P, uint32_t max_count, const float* colors, GeomState g,
+int launch_tile_sort_gather(const Camera& cam, int P, uint32_t max_count, const GaussianSrc& src, GeomState g,
                             BinningState b, ImageState im, cudaStream_t stream);
 // raster_render.cu
 int launch_render_forward(const Camera& cam, BinningState b, ImageState im, float* out_color, cudaStream_t stream);
@@ -111,11 +159,10 @@ int launch_render_forward(const Camera& cam, BinningState b, ImageState im, floa
 int launch_render_backward(const Camera& cam, BinningState b, ImageState im, const float* dL_dpix,
                            float* dL_dmeans2D /*[P,3]*/, float4* dL_dconic_op /*[P] (x,y,w,opacity)*/,
                            float* dL_dcolors /*[P,3]*/, cudaStream_t stream);
-int launch_preprocess_backward(const Camera& cam, int P, const float* means3D, const int32_t* radii,
-                               const float* scales, const float* rots, const float* cov3D_precomp,
+int launch_preprocess_backward(const Camera& cam, int P, const GaussianSrc& src, const int32_t* radii,
                                const float4* conic_opacity, float* dL_dmeans2D /* in: moments, out: gradient */,
-                               const float4* dL_dconic_op /* moments */, float* dL_dopacity, float* dL_dmeans3D,
-                               float* dL_dcov3D, float* dL_dscales, float* dL_drots, cudaStream_t stream);
+                               const float4* dL_dconic_op /* moments */, const float* dL_dcolors,
+                               const GaussianGrads& out, cudaStream_t stream);
 // sh.cu
 int launch_sh_forward(int P, int deg, int M, const float* campos3, const float* means3D, const float* shs,
                       const int32_t* radii, float* rgb, uint8_t* clamped, cudaStream_t stream);

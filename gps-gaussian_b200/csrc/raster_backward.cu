@@ -210,12 +210,9 @@ int launch_render_backward(const Camera& cam, BinningState b, ImageState im, con
 
 // A.7 + A.8 fused: per Gaussian, (dL/dmean2D, dL/dconic) -> dL/d{mean3D, cov3D, scale, rotation}.
 __global__ void __launch_bounds__(256) preprocess_backward_kernel(
-    const __grid_constant__ Camera cam, int P, const float* __restrict__ means3D, const int32_t* __restrict__ radii,
-    const float* __restrict__ scales, const float* __restrict__ rots, const float* __restrict__ cov3D_precomp,
+    const __grid_constant__ Camera cam, int P, const GaussianSrc src, const int32_t* __restrict__ radii,
     const float4* __restrict__ conic_opacity, const float* dL_dmeans2D, float* dL_dmeans2D_out,
-    const float4* __restrict__ dL_dconic_op, float* __restrict__ dL_dopacity,
-    float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dscales,
-    float* __restrict__ dL_drots) {
+    const float4* __restrict__ dL_dconic_op, const float* __restrict__ dL_dcolors, const GaussianGrads out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     float dm[3] = {0.f, 0.f, 0.f}, dsc[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
@@ -224,7 +221,10 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
     if (radii[i] > 0) {
         const float* view = cam.view;
         const float* proj = cam.proj;
-        const float x = means3D[3 * i], y = means3D[3 * i + 1], z = means3D[3 * i + 2];
+        float x, y, z, sc3[3] = {0.f, 0.f, 0.f}, opac_in;
+        float4 qin = make_float4(0.f, 0.f, 0.f, 0.f);
+        src_geom(src, i, x, y, z, sc3, qin, opac_in);            // radii > 0 implies a valid Gaussian
+        const float* cov3D_precomp = src.cov3D_precomp;
         // The compositing backward accumulated raw moments of s = G*dL/dG (see render_backward_kernel):
         //   dL_dmeans2D[i] = (sum s*dx, sum s*dy), dL_dconic_op[i] = (sum s*dx^2, sum s*dx*dy, sum s*dy^2, sum s).
         // With conic (cx,cy,cz) and opacity o:  dG/ddelx = -G (cx dx + cy dy), dG/dcx = -G dx^2 / 2, ...
@@ -244,12 +244,12 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
 #pragma unroll
             for (int k = 0; k < 6; ++k) c6[k] = cov3D_precomp[6 * i + k];
         } else {
-            qr = rots[4 * i]; qx = rots[4 * i + 1]; qy = rots[4 * i + 2]; qz = rots[4 * i + 3];
+            qr = qin.x; qx = qin.y; qy = qin.z; qz = qin.w;
             R[0][0] = 1.f - 2.f * (qy * qy + qz * qz); R[0][1] = 2.f * (qx * qy - qr * qz); R[0][2] = 2.f * (qx * qz + qr * qy);
             R[1][0] = 2.f * (qx * qy + qr * qz); R[1][1] = 1.f - 2.f * (qx * qx + qz * qz); R[1][2] = 2.f * (qy * qz - qr * qx);
             R[2][0] = 2.f * (qx * qz - qr * qy); R[2][1] = 2.f * (qy * qz + qr * qx); R[2][2] = 1.f - 2.f * (qx * qx + qy * qy);
-            sv[0] = cam.scale_modifier * scales[3 * i]; sv[1] = cam.scale_modifier * scales[3 * i + 1];
-            sv[2] = cam.scale_modifier * scales[3 * i + 2];
+            sv[0] = cam.scale_modifier * sc3[0]; sv[1] = cam.scale_modifier * sc3[1];
+            sv[2] = cam.scale_modifier * sc3[2];
             // Sigma(a,b) = sum_i R(a,i) s_i^2 R(b,i)
             float N[3][3];
 #pragma unroll
@@ -362,36 +362,45 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
             dq[3] = 2.f * (-2.f * qz * dR[0][0] - qr * dR[0][1] + qx * dR[0][2] + qr * dR[1][0] - 2.f * qz * dR[1][1] + qy * dR[1][2] + qx * dR[2][0] + qy * dR[2][1]);
         }
     }
-    dL_dopacity[i] = dop;
     dL_dmeans2D_out[3 * i] = dm2[0];      // final d/dmeans2D (NDC-scaled, as upstream) replaces the moment scratch
     dL_dmeans2D_out[3 * i + 1] = dm2[1];
+    if (src.S2 == 0) {
+        out.dopacity[i] = dop;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) dL_dmeans3D[3 * i + k] = dm[k];
-    if (dL_dcov3D) {
+        for (int k = 0; k < 3; ++k) out.dmeans3D[3 * i + k] = dm[k];
+        if (out.dcov3D) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) dL_dcov3D[6 * i + k] = dcov[k];
-    }
-    if (dL_dscales) {
+            for (int k = 0; k < 6; ++k) out.dcov3D[6 * i + k] = dcov[k];
+        }
+        if (out.dscales) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) dL_dscales[3 * i + k] = dsc[k];
-    }
-    if (dL_drots) {
+            for (int k = 0; k < 3; ++k) out.dscales[3 * i + k] = dsc[k];
+        }
+        if (out.drots) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dL_drots[4 * i + k] = dq[k];
+            for (int k = 0; k < 4; ++k) out.drots[4 * i + k] = dq[k];
+        }
+    } else {   // map mode: gradients in the layout of the source maps (zero for invalid / culled pixels)
+        const int v = i >= src.S2 ? 1 : 0;
+        const size_t px = (size_t)(i - v * src.S2), S2 = (size_t)src.S2;
+        out.dopac[v][px] = dop;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            out.dxyz[v][3 * px + k] = dm[k];
+            out.dscale[v][k * S2 + px] = dsc[k];
+            out.dimg[v][k * S2 + px] = 0.5f * dL_dcolors[3 * (size_t)i + k];    // colours were img*0.5+0.5
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out.drot[v][k * S2 + px] = dq[k];
     }
 }
 
-int launch_preprocess_backward(const Camera& cam, int P, const float* means3D, const int32_t* radii,
-                               const float* scales, const float* rots, const float* cov3D_precomp,
+int launch_preprocess_backward(const Camera& cam, int P, const GaussianSrc& src, const int32_t* radii,
                                const float4* conic_opacity, float* dL_dmeans2D, const float4* dL_dconic_op,
-                               float* dL_dopacity, float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales,
-                               float* dL_drots, cudaStream_t stream) {
+                               const float* dL_dcolors, const GaussianGrads& out, cudaStream_t stream) {
     if (P <= 0) return GPSG_OK;
-    preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(cam, P, means3D, radii, scales, rots,
-                                                                   cov3D_precomp, conic_opacity, dL_dmeans2D,
-                                                                   dL_dmeans2D, dL_dconic_op,
-                                                                   dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dscales,
-                                                                   dL_drots);
+    preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(cam, P, src, radii, conic_opacity, dL_dmeans2D,
+                                                                   dL_dmeans2D, dL_dconic_op, dL_dcolors, out);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
 }

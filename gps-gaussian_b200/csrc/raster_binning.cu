@@ -157,11 +157,12 @@ int launch_bucket_scatter(const Camera& cam, int P, const int32_t* radii, GeomSt
     return GPSG_OK;
 }
 
-__device__ __forceinline__ void slab_entry(uint32_t id, const float* __restrict__ colors, const GeomState& g, float4& A,
+__device__ __forceinline__ void slab_entry(uint32_t id, const GaussianSrc& src, const GeomState& g, float4& A,
                                            float4& B, float4& C) {
     const float2 xy = g.means2D[id];
     const float4 co = g.conic_opacity[id];
-    const float r = colors[3 * id], gg = colors[3 * id + 1], bb = colors[3 * id + 2];
+    float r, gg, bb;
+    src_color(src, id, r, gg, bb);
     // Conservative screen-space half-extents of the region where alpha = o*exp(power) can reach 1/255:
     // power >= -tau, tau = ln(255 o)  <=>  d^T Conic d <= 2 tau  -> bounding box sqrt(2 tau * Sigma_xx/yy),
     // Sigma = Conic^-1.  Used only to SKIP work that the per-pixel tests would reject anyway (results unchanged).
@@ -200,7 +201,7 @@ struct TileSort {
     //    (id + depth) radix sort, so degenerate inputs (thousands of identical depths) stay correct and bounded.
     static constexpr int kMaxRun = 16;
     __device__ static void run(Smem& sm, int* flags, const unsigned long long* __restrict__ src, int n, int id_bits,
-                               uint32_t tile, size_t out0, const float* __restrict__ colors, const GeomState& g,
+                               uint32_t tile, size_t out0, const GaussianSrc& src_in, const GeomState& g,
                                const BinningState& b) {
         unsigned long long keys[ITEMS];
         unsigned long long kmin = ~0ull, kmax = 0ull;
@@ -283,7 +284,7 @@ struct TileSort {
                 b.keys[o] = tile_hi | (keys[k] >> 32);
                 b.vals[o] = id;
                 float4 A, B, C;
-                slab_entry(id, colors, g, A, B, C);
+                slab_entry(id, src_in, g, A, B, C);
                 b.slabA[o] = A;
                 b.slabB[o] = B;
                 b.slabC[o] = C;
@@ -297,7 +298,7 @@ struct TileSort {
 // empty, so the planned (sync-free) path can always launch it.  Two kernels so that the common case is not held at
 // the register / shared-memory footprint of the rare one.
 template <bool BIG>
-__global__ void __launch_bounds__(256, BIG ? 1 : 4) tile_sort_gather_kernel(const float* __restrict__ colors, GeomState g,
+__global__ void __launch_bounds__(256, BIG ? 1 : 4) tile_sort_gather_kernel(const GaussianSrc colors, GeomState g,
                                                                             BinningState b, ImageState im, int id_bits) {
     __shared__ int flags[4];
     if (im.totals[2]) return;                   // planned mode overflow
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(256, BIG ? 1 : 4) tile_sort_gather_kernel(cons
     }
 }
 
-int launch_tile_sort_gather(const Camera& cam, int P, uint32_t max_count, const float* colors, GeomState g,
+int launch_tile_sort_gather(const Camera& cam, int P, uint32_t max_count, const GaussianSrc& colors, GeomState g,
                             BinningState b, ImageState im, cudaStream_t stream) {
     int id_bits = 1;
     while (id_bits < 32 && (1ll << id_bits) < (long long)P) ++id_bits;
@@ -344,7 +345,7 @@ int launch_tile_sort_gather(const Camera& cam, int P, uint32_t max_count, const 
 }
 
 // One thread per sorted pair: tile-range detection + parameter gather into the slabs.
-__global__ void __launch_bounds__(256) gather_ranges_kernel(size_t N, const float* __restrict__ colors, GeomState g,
+__global__ void __launch_bounds__(256) gather_ranges_kernel(size_t N, const GaussianSrc colors, GeomState g,
                                                             BinningState b, ImageState im) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(256) gather_ranges_kernel(size_t N, const floa
     b.slabC[i] = C;
 }
 
-int launch_gather_ranges(const Camera& cam, size_t N, const float* colors, GeomState g, BinningState b, ImageState im,
+int launch_gather_ranges(const Camera& cam, size_t N, const GaussianSrc& colors, GeomState g, BinningState b, ImageState im,
                          cudaStream_t stream) {
     GPSG_CUDA(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)cam.grid_x * cam.grid_y, stream));
     if (N == 0) return GPSG_OK;

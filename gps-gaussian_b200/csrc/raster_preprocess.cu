@@ -33,13 +33,8 @@ __device__ __forceinline__ void cov3d_from_scale_rot(const float s0_, const floa
 }
 
 __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__ Camera cam, int P,
-                                                         const float* __restrict__ means3D,
-                                                         const float* __restrict__ scales,
-                                                         const float* __restrict__ rots,
-                                                         const float* __restrict__ opacities,
-                                                         const float* __restrict__ cov3D_precomp,
-                                                         int32_t* __restrict__ radii, GeomState g, ImageState im,
-                                                         uint32_t capacity) {
+                                                         const GaussianSrc src, int32_t* __restrict__ radii,
+                                                         GeomState g, ImageState im, uint32_t capacity) {
     __shared__ uint32_t sh_cnt[kBoxBins];
     __shared__ int s_bb[4];
     __shared__ int s_last;
@@ -51,7 +46,9 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
     int32_t out_radius = 0;
     uint32_t out_tiles = 0;
     if (i < P) do {
-        const float x = means3D[3 * i], y = means3D[3 * i + 1], z = means3D[3 * i + 2];
+        float x, y, z, sc3[3], opac;
+        float4 q;
+        if (!src_geom(src, i, x, y, z, sc3, q, opac)) break;     // map mode: invalid pixel
         const float* view = cam.view;
         const float* proj = cam.proj;
         const float tvx = ((view[0] * x + view[4] * y) + view[8] * z) + view[12];
@@ -64,12 +61,11 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
         const float pw = 1.0f / (hw + 0.0000001f);
         const float ndcx = hx * pw, ndcy = hy * pw;
         float c6[6];
-        if (cov3D_precomp) {
+        if (src.cov3D_precomp) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) c6[k] = cov3D_precomp[6 * i + k];
+            for (int k = 0; k < 6; ++k) c6[k] = src.cov3D_precomp[6 * i + k];
         } else {
-            const float4 q = make_float4(rots[4 * i], rots[4 * i + 1], rots[4 * i + 2], rots[4 * i + 3]);
-            cov3d_from_scale_rot(scales[3 * i], scales[3 * i + 1], scales[3 * i + 2], cam.scale_modifier, q, c6);
+            cov3d_from_scale_rot(sc3[0], sc3[1], sc3[2], cam.scale_modifier, q, c6);
         }
         // EWA projection: A = J * Wrot (2x3), cov2D = A Sigma A^T
         const float limx = 1.3f * cam.tanfovx, limy = 1.3f * cam.tanfovy;
@@ -114,7 +110,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
         if (area == 0) break;
         g.depths[i] = tvz;
         g.means2D[i] = make_float2(px, py);
-        g.conic_opacity[i] = make_float4(conx, cony, conz, opacities[i]);
+        g.conic_opacity[i] = make_float4(conx, cony, conz, opac);
         out_radius = my_radius;
         out_tiles = (uint32_t)area;
         bx0 = rx0; by0 = ry0; bx1 = rx1; by1 = ry1;
@@ -151,12 +147,10 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
     }
 }
 
-int launch_preprocess(const Camera& cam, int P, const float* means3D, const float* scales, const float* rots,
-                      const float* opacities, const float* cov3D_precomp, int32_t* radii, GeomState g,
-                      ImageState im, uint32_t capacity, cudaStream_t stream) {
+int launch_preprocess(const Camera& cam, int P, const GaussianSrc& src, int32_t* radii, GeomState g, ImageState im,
+                      uint32_t capacity, cudaStream_t stream) {
     if (P <= 0) return GPSG_OK;
-    preprocess_kernel<<<(P + 255) / 256, 256, 0, stream>>>(cam, P, means3D, scales, rots, opacities, cov3D_precomp,
-                                                          radii, g, im, capacity);
+    preprocess_kernel<<<(P + 255) / 256, 256, 0, stream>>>(cam, P, src, radii, g, im, capacity);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
 }

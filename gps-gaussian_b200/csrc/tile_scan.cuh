@@ -17,10 +17,30 @@ __device__ __forceinline__ void tile_scan_block(int tiles, const ImageState& im,
     const int t0 = tid * per, t1 = min(tiles, t0 + per);
     if (tid == 0) s_max = 0;
     uint32_t sum = 0, mx = 0;
-    for (int t = t0; t < t1; ++t) {
-        const uint32_t c = __ldcg(&im.tile_count[t]);
-        sum += c;
-        mx = max(mx, c);
+    constexpr int kReg = 16;                  // counts of up to 16 tiles per thread stay in registers (4096 tiles / 256 thr)
+    uint32_t cnt[kReg];
+    const bool in_regs = per <= kReg;
+    if (in_regs) {
+        if ((per & 3) == 0 && t0 + per <= tiles) {   // 128-bit loads, all issued before the first use
+#pragma unroll
+            for (int q = 0; q < kReg / 4; ++q)
+                if (q * 4 < per) {
+                    const uint4 c4 = __ldcg(reinterpret_cast<const uint4*>(im.tile_count + t0) + q);
+                    cnt[q * 4] = c4.x; cnt[q * 4 + 1] = c4.y; cnt[q * 4 + 2] = c4.z; cnt[q * 4 + 3] = c4.w;
+                }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kReg; ++k) cnt[k] = (k < per && t0 + k < tiles) ? __ldcg(&im.tile_count[t0 + k]) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < kReg; ++k)
+            if (k < per && t0 + k < tiles) { sum += cnt[k]; mx = max(mx, cnt[k]); }
+    } else {
+        for (int t = t0; t < t1; ++t) {
+            const uint32_t c = __ldcg(&im.tile_count[t]);
+            sum += c;
+            mx = max(mx, c);
+        }
     }
     uint32_t v = sum;   // inclusive warp scan of the per-thread sums
 #pragma unroll
@@ -43,12 +63,18 @@ __device__ __forceinline__ void tile_scan_block(int tiles, const ImageState& im,
     if (lane == 0) atomicMax(&s_max, mx);
     __syncthreads();
     uint32_t run = v - sum + (warp ? ws[warp - 1] : 0u);   // exclusive prefix of this thread's first tile
-    for (int t = t0; t < t1; ++t) {
-        const uint32_t c = __ldcg(&im.tile_count[t]);
+    auto emit = [&](int t, uint32_t c) {
         im.ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);   // empty tiles stay (0,0) as upstream
         im.tile_cursor[t] = 0u;
         if (c > kBigTile) im.big_tiles[atomicAdd(&im.totals[3], 1u)] = (uint32_t)t;
         run += c;
+    };
+    if (in_regs) {
+#pragma unroll
+        for (int k = 0; k < kReg; ++k)
+            if (k < per && t0 + k < tiles) emit(t0 + k, cnt[k]);
+    } else {
+        for (int t = t0; t < t1; ++t) emit(t, __ldcg(&im.tile_count[t]));
     }
     if (tid == nthr - 1) {
         const uint32_t total = ws[nwarp - 1];

@@ -108,6 +108,27 @@ GPSG_API int gpsg_rasterize_backward(const GpsgRasterSettings* settings, int dev
                             float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drotations,
                             void* workspace);
 
+/* ---- fused map -> Gaussian ingest: the rasterizer behind lib/GaussianRender.py:5-39 (pts2render) -------------------
+ * Instead of boolean-mask gathering (10 `nonzero` host syncs per sample) and concatenating the two source views'
+ * pixel-aligned maps into [P,k] tensors, the maps are read in place: per view v in {0,1} (lmain, rmain), with S2 =
+ * pixels_per_view:  valid[v][S2] (uint8/bool), xyz[v][S2,3], img[v][3,S2] in [-1,1] (colour = img*0.5+0.5),
+ * rot[v][4,S2], scale[v][3,S2], opacity[v][1,S2].  Gaussian index = v*S2 + pixel; invalid pixels are culled.
+ * radii has 2*S2 entries.  Results (image, and gradients in map layout) equal the gather+render path. */
+GPSG_API int gpsg_rasterize_forward_maps(const GpsgRasterSettings* settings, int device, void* stream, int pixels_per_view,
+                                         const uint8_t* const* valid, const float* const* xyz, const float* const* img,
+                                         const float* const* rot, const float* const* scale, const float* const* opacity,
+                                         float* out_color, int32_t* radii, gpsg_alloc_fn geom_alloc, void* geom_user,
+                                         gpsg_alloc_fn binning_alloc, void* binning_user, gpsg_alloc_fn image_alloc,
+                                         void* image_user, int32_t* num_rendered);
+GPSG_API size_t gpsg_rasterize_backward_maps_workspace_bytes(int pixels_per_view);
+GPSG_API int gpsg_rasterize_backward_maps(const GpsgRasterSettings* settings, int device, void* stream, int pixels_per_view,
+                                          int32_t num_rendered, const uint8_t* const* valid, const float* const* xyz,
+                                          const float* const* img, const float* const* rot, const float* const* scale,
+                                          const float* const* opacity, const int32_t* radii, const void* geom_buffer,
+                                          const void* binning_buffer, const void* image_buffer, const float* dL_dout_color,
+                                          float* const* dL_dxyz, float* const* dL_dimg, float* const* dL_drot,
+                                          float* const* dL_dscale, float* const* dL_dopacity, void* workspace);
+
 /* ---- replaces _C.mark_visible : present[P] (uint8) = view-space z > 0.2 ---------------------- */
 GPSG_API int gpsg_mark_visible(int device, void* stream, int P, const float* means3D, const float* viewmatrix_host16,
                       uint8_t* present);

@@ -205,11 +205,8 @@ def test_dropin_autograd_module_matches_capi():
     assert vis.dtype == torch.bool and bool(vis.all())
 
 
-def test_mirrored_render_and_pts2render():
-    """reference-signature wrappers: render(data, idx, ...) and pts2render(data, bg_color) on a synthetic pair."""
-    from gps_gaussian_b200.GaussianRender import pts2render
-    res = 128
-    sc = synth.stereo_pair_scene(res, keep_maps=True)
+def _stereo_data(res, requires_grad=False, seed=None):
+    sc = synth.stereo_pair_scene(res, keep_maps=True) if seed is None else synth.stereo_pair_scene(res, keep_maps=True, seed=seed)
     cam = sc["cam"]
     data = {"novel_view": {"FovX": torch.tensor([cam["FovX"]], dtype=torch.float64),
                            "FovY": torch.tensor([cam["FovY"]], dtype=torch.float64),
@@ -218,15 +215,44 @@ def test_mirrored_render_and_pts2render():
                            "full_proj_transform": torch.tensor(cam["full_proj_transform"])[None],
                            "camera_center": torch.tensor(cam["camera_center"])[None]}}
     for name, vw in zip(("lmain", "rmain"), sc["views"]):
-        data[name] = {"img": torch.tensor(vw["img"]).cuda()[None], "pts_valid": torch.tensor(vw["valid"]).cuda()[None],
-                      "xyz": torch.tensor(vw["xyz"]).cuda()[None], "rot_maps": torch.tensor(vw["rot_maps"]).cuda()[None],
-                      "scale_maps": torch.tensor(vw["scale_maps"]).cuda()[None],
-                      "opacity_maps": torch.tensor(vw["opacity_maps"]).cuda()[None]}
+        T = lambda a: torch.tensor(a).cuda()[None].requires_grad_(requires_grad)
+        data[name] = {"img": T(vw["img"]), "pts_valid": torch.tensor(vw["valid"]).cuda()[None], "xyz": T(vw["xyz"]),
+                      "rot_maps": T(vw["rot_maps"]), "scale_maps": T(vw["scale_maps"]), "opacity_maps": T(vw["opacity_maps"])}
+    return sc, data
+
+
+def test_mirrored_render_and_pts2render():
+    """reference-signature wrappers: pts2render(data, bg_color) (fused map ingest) and the gather -> render(data, idx, ...)
+    data flow of the reference give the same image, equal to the oracle on the gathered Gaussians."""
+    from gps_gaussian_b200.GaussianRender import pts2render, pts2render_gather
+    res = 128
+    sc, data = _stereo_data(res)
     out = pts2render(data, [0.0, 0.0, 0.0])["novel_view"]["img_pred"]
     assert out.shape == (1, 3, res, res)
     _, ref = oracle_forward(sc, "f32")
     d = np.abs(_np(out[0]) - ref["color"]).max(0)
     assert (d > RGB_TOL).mean() < 5e-4 and d.max() < 1e-2
+    out2 = pts2render_gather(data, [0.0, 0.0, 0.0])["novel_view"]["img_pred"]
+    assert torch.equal(out, out2)                 # same Gaussians in the same order -> bit-identical image
+
+
+def test_fused_ingest_gradients_match_gather_path():
+    """d(loss)/d(maps) of the fused ingest == autograd through the reference's gather/concat/render data flow."""
+    from gps_gaussian_b200.GaussianRender import pts2render, pts2render_gather
+    res = 96
+    g = torch.randn(1, 3, res, res, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
+    grads = []
+    for fn in (pts2render, pts2render_gather):
+        _, data = _stereo_data(res, requires_grad=True, seed=4242)
+        out = fn(data, [0.1, 0.2, 0.3])["novel_view"]["img_pred"]
+        (out * g).sum().backward()
+        grads.append({(v, k): data[v][k].grad for v in ("lmain", "rmain") for k in ("xyz", "img", "rot_maps", "scale_maps", "opacity_maps")})
+    for key in grads[0]:
+        a, b = grads[0][key], grads[1][key]
+        assert a is not None and b is not None and a.shape == b.shape, key
+        scale = max(float(b.abs().max()), 1e-20)
+        per = (a - b).abs().flatten(1).max(0).values / scale if a.dim() > 1 else (a - b).abs() / scale
+        assert int((per > GRAD_TOL).sum()) <= 4 and float(per.max()) < 5e-2, (key, float(per.max()))
 
 
 def test_c2_full_size_parity_and_properties():
