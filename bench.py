@@ -292,6 +292,34 @@ def main():
     # cross-check the last image of the step against the device-resident render of the same scene
     e2e_err = float((out_host[V - 1].to(dev) - calls[V - 1].color).abs().max())
 
+    # ---- reference-signature pts2render(data, bg_color): fused map ingest vs the reference's gather data flow ----
+    from gps_gaussian_b200 import synth as _synth
+    from gps_gaussian_b200.GaussianRender import pts2render, pts2render_gather
+    scm = _synth.stereo_pair_scene(RES, seed=shard.unit_seeds(1314, V, rank)[0], keep_maps=True)
+    camm = scm["cam"]
+    pdata = {"novel_view": {"FovX": torch.tensor([camm["FovX"]], dtype=torch.float64),
+                            "FovY": torch.tensor([camm["FovY"]], dtype=torch.float64),
+                            "width": torch.tensor([RES]), "height": torch.tensor([RES]),
+                            "world_view_transform": torch.tensor(camm["world_view_transform"])[None],
+                            "full_proj_transform": torch.tensor(camm["full_proj_transform"])[None],
+                            "camera_center": torch.tensor(camm["camera_center"])[None]}}
+    for name, vw in zip(("lmain", "rmain"), scm["views"]):
+        Tm = lambda a: torch.tensor(a).to(dev)[None]
+        pdata[name] = {"img": Tm(vw["img"]), "pts_valid": torch.tensor(vw["valid"]).to(dev)[None], "xyz": Tm(vw["xyz"]),
+                       "rot_maps": Tm(vw["rot_maps"]), "scale_maps": Tm(vw["scale_maps"]), "opacity_maps": Tm(vw["opacity_maps"])}
+    p2r = {}
+    with torch.no_grad():
+        for nm, fn in (("fused_map_ingest", pts2render), ("gather_then_render", pts2render_gather)):
+            for _ in range(3):
+                fn(pdata, [0.0, 0.0, 0.0])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(20):
+                fn(pdata, [0.0, 0.0, 0.0])
+            torch.cuda.synchronize()
+            p2r[nm + "_ms"] = (time.perf_counter() - t0) * 1e3 / 20
+    del scm, pdata
+
     # ---- optional: forward+backward (training replay of the rasterizer) ----
     train = None
     if args.train:
@@ -359,7 +387,7 @@ def main():
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": b_comp, "kernel_ms": t_kernel * 1e3,
                          "note": "compositing is FP32/SFU-bound by design (about 130 FLOP/B); see DESIGN.md"},
-            "stages_ms": stages, "value_cuda_graph_replay": graph_value,
+            "stages_ms": stages, "value_cuda_graph_replay": graph_value, "pts2render_ms_per_call": p2r,
             "entry_point": "gpsg_rasterize_forward_planned (sync-free; verified bit-identical to gpsg_rasterize_forward)",
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
