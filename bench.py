@@ -112,6 +112,7 @@ def _cpu_oracle_views_per_sec(sc, n_views, warm=1):
     from oracle.raster_oracle import RasterOracle
     o = RasterOracle("f32")
     threads = o.max_threads()
+    o.set_threads(threads)          # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     run = lambda: o.forward(sc["means3D"], sc["colors"], sc["opacity"], sc["scales"], sc["rots"], sc["view"], sc["proj"],
                             sc["tanfovx"], sc["tanfovy"], sc["W"], sc["H"], sc["bg"], nthreads=threads)
     for _ in range(warm):

@@ -128,6 +128,9 @@ int SUFFIX(oracle_preprocess)(int P, int W, int H, const real* means3D, const re
     const int gx = (W + BLOCK_X - 1) / BLOCK_X, gy = (H + BLOCK_Y - 1) / BLOCK_Y;
     const real fx = (real)W / (RC(2.0) * tanfovx), fy = (real)H / (RC(2.0) * tanfovy);
     int nvis = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) reduction(+ : nvis)
+#endif
     for (int i = 0; i < P; ++i) {
         radii[i] = 0; tiles_touched[i] = 0;
         means2D[2 * i] = means2D[2 * i + 1] = 0; depth[i] = 0;
@@ -186,39 +189,50 @@ static int pair_cmp(const void* a, const void* b) {
 }
 
 /* depth32 = float32 depths (their BIT PATTERN is the low key half). keys/vals sized sum(tiles_touched).
- * ranges: 2*T uint32 (start,end). Returns number of pairs, or -1 on alloc failure. */
+ * ranges: 2*T uint32 (start,end). Returns number of pairs, or -1 on alloc failure.
+ * A stable sort on the 64-bit (tile, depth) key == stable counting sort by tile (emission order kept) followed by a
+ * stable sort of every tile's segment by depth; the second step runs one tile per OpenMP thread. */
 int64_t SUFFIX(oracle_bin)(int P, int W, int H, const int32_t* radii, const int32_t* rects, const float* depth32,
                            uint64_t* keys, uint32_t* vals, uint32_t* ranges) {
     const int gx = (W + BLOCK_X - 1) / BLOCK_X, gy = (H + BLOCK_Y - 1) / BLOCK_Y;
+    const int T = gx * gy;
+    int64_t* start = (int64_t*)calloc((size_t)T + 1, sizeof(int64_t));
+    if (!start) return -1;
     int64_t n = 0;
-    for (int i = 0; i < P; ++i)
-        if (radii[i] > 0) n += (int64_t)(rects[4 * i + 2] - rects[4 * i]) * (rects[4 * i + 3] - rects[4 * i + 1]);
+    for (int i = 0; i < P; ++i) {
+        if (radii[i] <= 0) continue;
+        for (int y = rects[4 * i + 1]; y < rects[4 * i + 3]; ++y)
+            for (int x = rects[4 * i]; x < rects[4 * i + 2]; ++x) { ++start[y * gx + x + 1]; ++n; }
+    }
+    for (int t = 0; t < T; ++t) start[t + 1] += start[t];
     pair_t* tmp = (pair_t*)malloc(sizeof(pair_t) * (size_t)(n > 0 ? n : 1));
-    if (!tmp) return -1;
-    int64_t off = 0;
+    int64_t* cur = (int64_t*)malloc(sizeof(int64_t) * (size_t)T);
+    if (!tmp || !cur) { free(start); free(tmp); free(cur); return -1; }
+    memcpy(cur, start, sizeof(int64_t) * (size_t)T);
+    uint32_t pos = 0;
     for (int i = 0; i < P; ++i) {
         if (radii[i] <= 0) continue;
         uint32_t dbits; memcpy(&dbits, depth32 + i, 4);
         for (int y = rects[4 * i + 1]; y < rects[4 * i + 3]; ++y)
             for (int x = rects[4 * i]; x < rects[4 * i + 2]; ++x) {
-                uint64_t key = (uint64_t)(uint32_t)(y * gx + x);
-                key = (key << 32) | dbits;
-                tmp[off].key = key; tmp[off].val = (uint32_t)i; tmp[off].pos = (uint32_t)off; ++off;
+                const int t = y * gx + x;
+                pair_t* e = tmp + cur[t]++;
+                e->key = ((uint64_t)(uint32_t)t << 32) | dbits; e->val = (uint32_t)i; e->pos = pos++;
             }
     }
-    qsort(tmp, (size_t)n, sizeof(pair_t), pair_cmp);
-    memset(ranges, 0, sizeof(uint32_t) * 2 * (size_t)gx * gy);
-    for (int64_t k = 0; k < n; ++k) {
-        keys[k] = tmp[k].key; vals[k] = tmp[k].val;
-        uint32_t t = (uint32_t)(tmp[k].key >> 32);
-        if (k == 0) ranges[2 * t] = 0;
-        else {
-            uint32_t pt = (uint32_t)(tmp[k - 1].key >> 32);
-            if (pt != t) { ranges[2 * pt + 1] = (uint32_t)k; ranges[2 * t] = (uint32_t)k; }
-        }
-        if (k == n - 1) ranges[2 * t + 1] = (uint32_t)n;
-    }
-    free(tmp);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 8)
+#endif
+    for (int t = 0; t < T; ++t)
+        if (start[t + 1] > start[t]) qsort(tmp + start[t], (size_t)(start[t + 1] - start[t]), sizeof(pair_t), pair_cmp);
+    memset(ranges, 0, sizeof(uint32_t) * 2 * (size_t)T);
+    for (int t = 0; t < T; ++t)
+        if (start[t + 1] > start[t]) { ranges[2 * t] = (uint32_t)start[t]; ranges[2 * t + 1] = (uint32_t)start[t + 1]; }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t k = 0; k < n; ++k) { keys[k] = tmp[k].key; vals[k] = tmp[k].val; }
+    free(tmp); free(cur); free(start);
     return n;
 }
 
@@ -555,9 +569,17 @@ void SUFFIX(oracle_mark_visible)(int P, const real* means3D, const real* view, u
     }
 }
 
+void SUFFIX(oracle_set_threads)(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int SUFFIX(oracle_max_threads)(void) {
 #ifdef _OPENMP
-    return omp_get_max_threads();
+    return omp_get_num_procs();
 #else
     return 1;
 #endif

@@ -56,7 +56,11 @@ class RasterOracle:
         return x
 
     def max_threads(self):
+        """Host cores available to OpenMP (not OMP_NUM_THREADS, which torchrun forces to 1)."""
         return int(self._fn("oracle_max_threads")())
+
+    def set_threads(self, n):
+        self._fn("oracle_set_threads")(C.c_int(int(n)))
 
     def sh_colors(self, means3D, campos, shs, deg):
         """SH -> RGB (+0.5, clamp at 0).  shs: [P, M, 3].  Returns (colors[P,3], clamped[P,3] bool)."""
