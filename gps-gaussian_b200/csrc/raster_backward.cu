@@ -98,46 +98,44 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32) render_backward_kernel(c
             const float4* __restrict__ SC = ring.C[s];
             // Survivors are taken two at a time (deeper one first): their 2 x 9 per-pixel gradient terms go straight
             // into x[0..7]/x[8..15] (dmx,dmy,dcx,dcy,dcw,dop,dr,dg) and y[0..1] (db), then one butterfly per pair.
-            auto eval = [&](int j, float* xo, float& yo) -> bool {
-                bool active = (start + j) < last_contributor;   // implies inside
-#pragma unroll
-                for (int i = 0; i < 8; ++i) xo[i] = 0.f;
-                yo = 0.f;
-                if (active) {
-                    const float2 xy = *reinterpret_cast<const float2*>(&SA[j]);
-                    const float4 q = SB[j];
-                    const float dx = xy.x - pixfx, dy = xy.y - pixfy;
-                    const float p = fmaf(q.z * dy, dy, fmaf(q.x, dx, q.y * dy) * dx);   // log2e * power
-                    const float G = ex2_approx(p);
-                    const float alpha = fminf(0.99f, q.w * G);
-                    active = !(p > 0.0f) && !(alpha < 1.0f / 255.0f);
-                    if (active) {
-                        const float4 c = SC[j];
-                        const float inv1ma = __frcp_rn(1.0f - alpha);
-                        T = T * inv1ma;
-                        const float dchannel_dcolor = alpha * T;
-                        accum0 = fmaf(last_alpha, lastc0 - accum0, accum0); lastc0 = c.x;
-                        accum1 = fmaf(last_alpha, lastc1 - accum1, accum1); lastc1 = c.y;
-                        accum2 = fmaf(last_alpha, lastc2 - accum2, accum2); lastc2 = c.z;
-                        float dL_dalpha = (c.x - accum0) * g0;
-                        dL_dalpha = fmaf(c.y - accum1, g1, dL_dalpha);
-                        dL_dalpha = fmaf(c.z - accum2, g2, dL_dalpha);
-                        xo[6] = dchannel_dcolor * g0; xo[7] = dchannel_dcolor * g1; yo = dchannel_dcolor * g2;
-                        dL_dalpha *= T;
-                        last_alpha = alpha;
-                        dL_dalpha = fmaf(-T_final * inv1ma, bg_dot, dL_dalpha);
-                        // Raw moments of s = G * dL/dG over the pixels (converted to d/dmean2D, d/dconic, d/dopacity once
-                        // per Gaussian in preprocess_backward):  xo[0..5] = s * (dx, dy, dx^2, dx*dy, dy^2, 1)
-                        const float sG = G * (q.w * dL_dalpha);
-                        const float sx = sG * dx, sy = sG * dy;
-                        xo[0] = sx;
-                        xo[1] = sy;
-                        xo[2] = sx * dx;
-                        xo[3] = sx * dy;
-                        xo[4] = sy * dy;
-                        xo[5] = sG;
-                    }
-                }
+            // Straight-line, predicated evaluation (as in the forward): the gradient tail runs whenever any lane is
+            // active, so per-lane branches would only add BSSY/BSYNC/BRA and register shuffling at the merge points.
+            auto eval = [&](int j, bool enable, float* xo, float& yo) -> bool {
+                const float2 xy = *reinterpret_cast<const float2*>(&SA[j]);
+                const float4 q = SB[j];
+                const float4 c = SC[j];
+                const float dx = xy.x - pixfx, dy = xy.y - pixfy;
+                const float p = fmaf(q.z * dy, dy, fmaf(q.x, dx, q.y * dy) * dx);   // log2e * power
+                const float G = ex2_approx(p);
+                const float alpha = fminf(0.99f, q.w * G);
+                const bool active = enable && (start + j) < last_contributor && !(p > 0.0f) && !(alpha < 1.0f / 255.0f);
+                const float inv1ma = __frcp_rn(1.0f - alpha);
+                const float Tn = T * inv1ma;
+                const float a0 = fmaf(last_alpha, lastc0 - accum0, accum0);
+                const float a1 = fmaf(last_alpha, lastc1 - accum1, accum1);
+                const float a2 = fmaf(last_alpha, lastc2 - accum2, accum2);
+                float dL_dalpha = (c.x - a0) * g0;
+                dL_dalpha = fmaf(c.y - a1, g1, dL_dalpha);
+                dL_dalpha = fmaf(c.z - a2, g2, dL_dalpha);
+                dL_dalpha = fmaf(dL_dalpha, Tn, (-T_final * inv1ma) * bg_dot);
+                // Raw moments of s = G * dL/dG over the pixels (converted to d/dmean2D, d/dconic, d/dopacity once
+                // per Gaussian in preprocess_backward):  xo[0..5] = s * (dx, dy, dx^2, dx*dy, dy^2, 1)
+                const float sG = active ? G * (q.w * dL_dalpha) : 0.0f;
+                const float dch = active ? alpha * Tn : 0.0f;
+                const float sx = sG * dx, sy = sG * dy;
+                xo[0] = sx;
+                xo[1] = sy;
+                xo[2] = sx * dx;
+                xo[3] = sx * dy;
+                xo[4] = sy * dy;
+                xo[5] = sG;
+                xo[6] = dch * g0;
+                xo[7] = dch * g1;
+                yo = dch * g2;
+                T = active ? Tn : T;
+                accum0 = active ? a0 : accum0; accum1 = active ? a1 : accum1; accum2 = active ? a2 : accum2;
+                lastc0 = active ? c.x : lastc0; lastc1 = active ? c.y : lastc1; lastc2 = active ? c.z : lastc2;
+                last_alpha = active ? alpha : last_alpha;
                 return active;
             };
             for (int base = ((n - 1) >> 5) << 5; base >= 0; base -= 32) {
@@ -153,20 +151,12 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32) render_backward_kernel(c
                     float x[16], y[2];
                     const int bitA = 31 - __clz(m);
                     m &= ~(1u << bitA);
-                    const int jA = base + bitA;
-                    bool act = eval(jA, x, y[0]);
-                    int jB = jA;
                     const bool two = m != 0;
-                    if (two) {
-                        const int bitB = 31 - __clz(m);
-                        m &= ~(1u << bitB);
-                        jB = base + bitB;
-                        act |= eval(jB, x + 8, y[1]);
-                    } else {
-#pragma unroll
-                        for (int i = 8; i < 16; ++i) x[i] = 0.f;
-                        y[1] = 0.f;
-                    }
+                    const int bitB = two ? 31 - __clz(m) : bitA;
+                    m &= ~(two ? (1u << bitB) : 0u);
+                    const int jA = base + bitA, jB = base + bitB;
+                    bool act = eval(jA, true, x, y[0]);
+                    act |= eval(jB, two, x + 8, y[1]);        // disabled second slot contributes exact zeros
                     if (!__any_sync(0xffffffffu, act)) continue;
                     rs_step<16>(x, lane, 16);
                     rs_step<8>(x, lane, 8);
