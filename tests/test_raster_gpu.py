@@ -357,3 +357,18 @@ def test_sh_colour_branch_forward_backward(deg, M):
     for got, exp in ((sh_t.grad, dsh), (m.grad, want["dL_dmeans3D"]), (op.grad, want["dL_dopacity"]), (s_.grad, want["dL_dscales"])):
         per = _grad_err(_np(got), exp)
         assert int((per > GRAD_TOL).sum()) <= max(2, int(1e-3 * P)) and per.max() < 5e-2
+
+
+def test_2048_render_resolution_forward_and_backward():
+    """The real pipeline renders at 2 x src_res = 2048^2 (use_hr_img, reference config/stage2.yaml:15): 16384 tiles
+    (tile-scan generic path, larger tile grid for the CTA-local histograms)."""
+    sc = synth.stereo_pair_scene(512, render_res=2048, seed=77)
+    assert sc["W"] == 2048 and sc["means3D"].shape[0] > 100_000
+    rc, ref = _assert_forward_parity(sc)
+    g = torch.randn(3, 2048, 2048, device="cuda", generator=torch.Generator("cuda").manual_seed(9))
+    got = rc.backward(g)
+    o, ref64 = oracle_forward(sc, "f64")
+    want = o.backward(ref64, _np(g).astype(np.float64))
+    for k_got, k_ref in (("dL_dmeans3D", "dL_dmeans3D"), ("dL_dscales", "dL_dscales"), ("dL_dcolors", "dL_dcolors")):
+        per = _grad_err(_np(got[k_got]), want[k_ref])
+        assert int((per > GRAD_TOL).sum()) <= max(2, int(1e-3 * rc.P)) and per.max() < 5e-2, k_got
