@@ -367,8 +367,11 @@ def test_2048_render_resolution_forward_and_backward():
     rc, ref = _assert_forward_parity(sc)
     g = torch.randn(3, 2048, 2048, device="cuda", generator=torch.Generator("cuda").manual_seed(9))
     got = rc.backward(g)
-    o, ref64 = oracle_forward(sc, "f64")
-    want = o.backward(ref64, _np(g).astype(np.float64))
-    for k_got, k_ref in (("dL_dmeans3D", "dL_dmeans3D"), ("dL_dscales", "dL_dscales"), ("dL_dcolors", "dL_dcolors")):
-        per = _grad_err(_np(got[k_got]), want[k_ref])
-        assert int((per > GRAD_TOL).sum()) <= max(2, int(1e-3 * rc.P)) and per.max() < 5e-2, k_got
+    # splats are ~4x larger in pixels here (512^2 sources rendered at 2048^2), so many more (pixel, Gaussian) pairs sit
+    # near a hard threshold: same-precision (fp32) oracle at the standard bound, fp64 oracle with a wider flip allowance
+    for dt, frac in (("f32", 1e-3), ("f64", 5e-3)):
+        o, refo = oracle_forward(sc, dt)
+        want = o.backward(refo, _np(g).astype(o.np))
+        for k_got, k_ref in (("dL_dmeans3D", "dL_dmeans3D"), ("dL_dscales", "dL_dscales"), ("dL_dcolors", "dL_dcolors")):
+            per = _grad_err(_np(got[k_got]), want[k_ref])
+            assert int((per > GRAD_TOL).sum()) <= max(2, int(frac * rc.P)) and per.max() < 5e-2, (dt, k_got, int((per > GRAD_TOL).sum()))
