@@ -4,6 +4,7 @@ One process per GPU (`torch.distributed`, NCCL on GPUs / gloo in the CPU tests).
 collective: each rank renders its own view-pairs; the only communication is a barrier and a MAX-reduce of the
 elapsed time (so throughput = all units / slowest rank), plus an optional gather of small per-rank results."""
 import os
+import sys
 
 import torch
 import torch.distributed as dist
@@ -23,7 +24,21 @@ def init(backend=None, device=None):
         # NCCL prints its version banner to STDOUT at INFO/VERSION level; bench.py's stdout must be one JSON line
         os.environ["NCCL_DEBUG"] = os.environ.get("GPSG_NCCL_DEBUG", "WARN")
         kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
-        dist.init_process_group(backend, rank=rank, world_size=ws, **kw)
+        # NCCL prints its version banner to STDOUT while the communicator is created; bench.py's stdout must carry
+        # exactly one JSON line, so fd 1 is pointed at stderr for the duration of the (eager) initialisation.
+        sys.stdout.flush()
+        saved = os.dup(1)
+        try:
+            os.dup2(2, 1)
+            dist.init_process_group(backend, rank=rank, world_size=ws, **kw)
+            if backend == "nccl":
+                t = torch.zeros(1, device=device if device is not None else "cuda")
+                dist.all_reduce(t)                     # forces communicator creation now
+                torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     return rank, ws
 
 
