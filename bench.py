@@ -289,10 +289,10 @@ def main():
     value = total_views / (ms * 1e-3)
 
     # ---- end-to-end through the reference-facing call, HOST buffers, copies inside the timed region ----
+    from gps_gaussian_b200.pipeline import HostRenderPipeline, pack_host
     host = []
     for sc in scenes:
-        h = {k: torch.from_numpy(np.ascontiguousarray(sc[k], np.float32)).pin_memory()
-             for k in ("means3D", "colors", "rots", "scales", "opacity")}
+        h = pack_host(sc)            # one pinned buffer per view: [means3D | colors | rots | scales | opacity]
         cam = sc["cam"]
         data = {"novel_view": {"FovX": torch.tensor([cam["FovX"]], dtype=torch.float64),
                                "FovY": torch.tensor([cam["FovY"]], dtype=torch.float64),
@@ -301,9 +301,8 @@ def main():
                                "full_proj_transform": torch.tensor(cam["full_proj_transform"])[None].pin_memory(),
                                "camera_center": torch.tensor(cam["camera_center"])[None].pin_memory()}}
         host.append((h, data))
-    from gps_gaussian_b200.pipeline import HostRenderPipeline
     out_host = [torch.empty((3, RES, RES), dtype=torch.float32).pin_memory() for _ in range(V)]
-    h2d = sum(sum(t.numel() * 4 for t in h.values()) for h, _ in host)
+    h2d = sum(h[0].numel() * 4 for h, _ in host)
     d2h = V * out_host[0].numel() * 4
     pipe = HostRenderPipeline(dev, max(P), RES, RES)
     items = [(h, data, 0) for h, data in host]

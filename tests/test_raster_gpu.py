@@ -376,3 +376,37 @@ def test_2048_render_resolution_forward_and_backward():
             per = _grad_err(_np(got[k_got]), want[k_ref])
             cap = 5e-2 if dt == "f32" else 0.25      # one fp32-vs-fp64 T<1e-4 flip moves a large splat's gradient a lot
             assert int((per > GRAD_TOL).sum()) <= max(2, int(frac * rc.P)) and per.max() < cap, (dt, k_got, int((per > GRAD_TOL).sum()), float(per.max()))
+
+
+def test_randomised_parity_sweep():
+    """Small randomised sweep (image size, point count, spread, splat size, background): every integer output bit-exact."""
+    rng = np.random.default_rng(2024)
+    for k in range(8):
+        res = int(rng.integers(40, 300))
+        P = int(rng.integers(1, 6000))
+        sc = synth.random_cube_scene(P, res, spread=float(rng.uniform(0.2, 2.5)), scale_mul=float(rng.uniform(0.5, 8.0)),
+                                     bg=tuple(rng.uniform(0, 1, 3)), seed=int(rng.integers(1 << 30)))
+        _assert_forward_parity(sc)
+
+
+def test_pts2render_batch_of_two_and_host_pipeline():
+    """bs = 2 through the reference-signature pts2render, and the packed host-buffer pipeline == direct render."""
+    from gps_gaussian_b200.GaussianRender import pts2render
+    from gps_gaussian_b200.pipeline import HostRenderPipeline, pack_host
+    res = 96
+    sc0, d0 = _stereo_data(res, seed=11)
+    sc1, d1 = _stereo_data(res, seed=12)
+    data = {"novel_view": {k: torch.cat([d0["novel_view"][k], d1["novel_view"][k]]) for k in d0["novel_view"]}}
+    for v in ("lmain", "rmain"):
+        data[v] = {k: torch.cat([d0[v][k], d1[v][k]]) for k in d0[v]}
+    out = pts2render(data, [0.0, 0.0, 0.0])["novel_view"]["img_pred"]
+    assert out.shape == (2, 3, res, res)
+    for i, sc in enumerate((sc0, sc1)):
+        _, ref = oracle_forward(sc, "f32")
+        d = np.abs(_np(out[i]) - ref["color"]).max(0)
+        assert (d > RGB_TOL).mean() < 1e-3 and d.max() < 1e-2
+    pipe = HostRenderPipeline("cuda", max(sc0["means3D"].shape[0], sc1["means3D"].shape[0]), res, res)
+    items = [(pack_host(sc), dd, 0) for sc, dd in ((sc0, d0), (sc1, d1), (sc0, d0))]
+    outs = [torch.empty(3, res, res).pin_memory() for _ in items]
+    pipe.run(items, outs)
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[0].cuda(), out[0]) and torch.equal(outs[1].cuda(), out[1])
