@@ -25,6 +25,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_CPU_THREADS = None
 METRIC = "novel_views_per_sec_1024sq_500kgauss"
 UNIT = "views/s"
 RES = 1024
@@ -111,10 +112,23 @@ def _cpu_oracle_views_per_sec(sc, n_views, warm=1):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle.raster_oracle import RasterOracle
     o = RasterOracle("f32")
-    threads = o.max_threads()
-    o.set_threads(threads)          # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
-    run = lambda: o.forward(sc["means3D"], sc["colors"], sc["opacity"], sc["scales"], sc["rots"], sc["view"], sc["proj"],
-                            sc["tanfovx"], sc["tanfovy"], sc["W"], sc["H"], sc["bg"], nthreads=threads)
+    fwd = lambda nt: o.forward(sc["means3D"], sc["colors"], sc["opacity"], sc["scales"], sc["rots"], sc["view"], sc["proj"],
+                               sc["tanfovx"], sc["tanfovy"], sc["W"], sc["H"], sc["bg"], nthreads=nt)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm may use every host core.  Logical CPUs vs physical cores: pick
+    # whichever thread count is faster on this box (one probe render each), so the baseline is not handicapped.
+    global _CPU_THREADS
+    if _CPU_THREADS is None:
+        best = None
+        for nt in sorted({o.max_threads(), max(1, o.max_threads() // 2)}, reverse=True):
+            o.set_threads(nt)
+            fwd(nt)
+            t0 = time.perf_counter(); fwd(nt); dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, nt)
+        _CPU_THREADS = best[1]
+    threads = _CPU_THREADS
+    o.set_threads(threads)
+    run = lambda: fwd(threads)
     for _ in range(warm):
         run()
     t0 = time.perf_counter()
