@@ -20,28 +20,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-
-// ---- packed fp32 (sm_100: fma/mul/add .f32x2 -> SASS FFMA2/FMUL2/FADD2).  Measured on B200
-// (profiles/microbench): same FLOP/s as scalar FFMA at HALF the issue slots -- the compositing kernels are issue-bound.
-__device__ __forceinline__ unsigned long long f2_bits(float2 v) { return *reinterpret_cast<unsigned long long*>(&v); }
-__device__ __forceinline__ float2 bits_f2(unsigned long long b) { return *reinterpret_cast<float2*>(&b); }
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
-    return bits_f2(d);
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-    unsigned long long d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
-    return bits_f2(d);
-}
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-    unsigned long long d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
-    return bits_f2(d);
-}
-__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
-
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
