@@ -28,6 +28,7 @@ SOURCES = {
     "raster_backward.cu": [],
     "corr.cu": [],
     "sh.cu": [],
+    "unproject.cu": [],
 }
 
 

@@ -573,6 +573,29 @@ int gpsg_corr_lookup_pyramid_backward(int device, void* stream_, int dtype, int 
     return launch_corr_lookup_bwd(dtype, B, H, W1, grad_vols, widths, levels, coords, coords_sb, radius, grad_out, (cudaStream_t)stream_);
 }
 
+int gpsg_unproject_forward(int device, void* stream_, int B, int S, const float* flow_pred, const float* mask,
+                           int64_t mask_batch_stride, const float* intr, const float* extr, int extr_rows,
+                           const float* ref_intr, const float* Tf_x, float* depth, float* xyz, uint8_t* valid) {
+    GPSG_REQUIRE(B >= 0 && S >= 0 && extr_rows >= 3, "bad shape");
+    if ((int64_t)B * S * S == 0) return GPSG_OK;
+    GPSG_REQUIRE(flow_pred && mask && intr && extr && ref_intr && Tf_x && depth && xyz && valid, "NULL pointer");
+    GPSG_CUDA(cudaSetDevice(device));
+    return launch_unproject_fwd(B, S, flow_pred, mask, mask_batch_stride, intr, extr, extr_rows, ref_intr, Tf_x, depth, xyz,
+                                valid, (cudaStream_t)stream_);
+}
+
+int gpsg_unproject_backward(int device, void* stream_, int B, int S, const float* depth, const float* mask,
+                            int64_t mask_batch_stride, const float* intr, const float* extr, int extr_rows,
+                            const float* ref_intr, const float* Tf_x, const float* dL_dxyz, const float* dL_ddepth,
+                            float* dL_dflow) {
+    GPSG_REQUIRE(B >= 0 && S >= 0 && extr_rows >= 3, "bad shape");
+    if ((int64_t)B * S * S == 0) return GPSG_OK;
+    GPSG_REQUIRE(depth && mask && intr && extr && ref_intr && Tf_x && dL_dflow && (dL_dxyz || dL_ddepth), "NULL pointer");
+    GPSG_CUDA(cudaSetDevice(device));
+    return launch_unproject_bwd(B, S, depth, mask, mask_batch_stride, intr, extr, extr_rows, ref_intr, Tf_x, dL_dxyz,
+                                dL_ddepth, dL_dflow, (cudaStream_t)stream_);
+}
+
 int gpsg_profile_enable(int on) {
     g_prof.on = on != 0;
     return GPSG_OK;

@@ -169,6 +169,13 @@ int launch_sh_forward(int P, int deg, int M, const float* campos3, const float* 
 int launch_sh_backward(int P, int deg, int M, const float* campos3, const float* means3D, const float* shs,
                        const int32_t* radii, const uint8_t* clamped, const float* dL_dcolors, float* dL_dsh,
                        float* dL_dmeans3D, cudaStream_t stream);
+// unproject.cu
+int launch_unproject_fwd(int B, int S, const float* flow, const float* mask, int64_t mask_bs, const float* intr,
+                         const float* extr, int extr_rows, const float* ref_intr, const float* Tf_x, float* depth,
+                         float* xyz, uint8_t* valid, cudaStream_t stream);
+int launch_unproject_bwd(int B, int S, const float* depth, const float* mask, int64_t mask_bs, const float* intr,
+                         const float* extr, int extr_rows, const float* ref_intr, const float* Tf_x,
+                         const float* dL_dxyz, const float* dL_ddepth, float* dL_dflow, cudaStream_t stream);
 // corr.cu
 int launch_corr_fwd(int dtype, int B, int H, int W1, int W2, const void* vol, int64_t sb, int64_t sh, int64_t sw1,
                     const float* coords, int64_t csb, int r, void* out, cudaStream_t stream);

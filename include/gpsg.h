@@ -182,6 +182,18 @@ GPSG_API int gpsg_corr_lookup_pyramid_backward(int device, void* stream, int dty
                                                void* const* grad_vols, const int32_t* widths, int levels,
                                                const float* coords, int64_t coords_sb, int radius, const void* grad_out);
 
+/* ---- fused unprojection, the producer of the rasterizer's means3D (reference lib/network.py:64-69 -> lib/utils.py:87-119:
+ * flow2depth + depth2pc + `depth != 0`).  flow_pred[B,1,S,S], mask[B,C,S,S] (channel 0 used; batch stride in elements),
+ * intr[B,3,3], extr[B,extr_rows>=3,4], ref_intr[B,3,3], Tf_x[B]  ->  depth[B,1,S,S], xyz[B,S*S,3], valid[B,S*S] (uint8).
+ * Backward: dL_dxyz (and optionally an incoming dL_ddepth) -> dL_dflow[B,1,S,S]. */
+GPSG_API int gpsg_unproject_forward(int device, void* stream, int B, int S, const float* flow_pred, const float* mask,
+                                    int64_t mask_batch_stride, const float* intr, const float* extr, int extr_rows,
+                                    const float* ref_intr, const float* Tf_x, float* depth, float* xyz, uint8_t* valid);
+GPSG_API int gpsg_unproject_backward(int device, void* stream, int B, int S, const float* depth, const float* mask,
+                                     int64_t mask_batch_stride, const float* intr, const float* extr, int extr_rows,
+                                     const float* ref_intr, const float* Tf_x, const float* dL_dxyz,
+                                     const float* dL_ddepth, float* dL_dflow);
+
 /* ---- measurement hooks (used by bench.py; off by default) -----------------------------------
  * When enabled, every stage of the forward/backward is bracketed by CUDA events on the launching stream.
  * gpsg_profile_read() synchronises, then returns for stage i: total_ms[i] (summed over the calls since the last
