@@ -364,7 +364,25 @@ def main():
                 fn(pdata, [0.0, 0.0, 0.0])
             torch.cuda.synchronize()
             p2r[nm + "_ms"] = (time.perf_counter() - t0) * 1e3 / 20
-    del scm, pdata
+    # the chain in front of it: fused unprojection (flow -> depth -> xyz, pts_valid) for both source views at 1024^2
+    from gps_gaussian_b200.unproject import flow2xyz
+    udata = {}
+    for name, vw in zip(("lmain", "rmain"), scm["views"]):
+        inv = np.where(vw["depth"] > 0, 1.0 / np.maximum(vw["depth"], 1e-6), 0.0).astype(np.float32)
+        Kt = torch.tensor(vw["K"].astype(np.float32))[None].to(dev)
+        udata[name] = {"flow_pred": torch.tensor(inv)[None, None].to(dev), "mask": torch.ones(1, 3, RES, RES, device=dev),
+                       "intr": Kt, "extr": torch.tensor(np.vstack([vw["E"], [0, 0, 0, 1]]).astype(np.float32))[None].to(dev),
+                       "ref_intr": Kt, "Tf_x": torch.tensor([1.0], device=dev)}
+    with torch.no_grad():
+        for _ in range(3):
+            flow2xyz(udata)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            flow2xyz(udata)
+        torch.cuda.synchronize()
+        p2r["fused_unproject_both_views_ms"] = (time.perf_counter() - t0) * 1e3 / 50
+    del scm, pdata, udata
 
     # ---- optional: forward+backward (training replay of the rasterizer) ----
     train = None
