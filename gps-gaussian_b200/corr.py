@@ -71,7 +71,8 @@ class _BuildPyramid(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        # Chain of avg_pool2d([1,2]) folded back to level 0, then the two contractions (library GEMMs via einsum).
+        # Chain of avg_pool2d([1,2]) folded back to level 0 (cheap elementwise torch ops), then the two contractions
+        # dF1 = F2 g^T, dF2 = F1 g in one sm_100a kernel each (gpsg_corr_build_backward).
         f1, f2 = ctx.saved_tensors
         B, D, H, W1 = f1.shape
         W2 = f2.shape[3]
@@ -86,9 +87,14 @@ class _BuildPyramid(torch.autograd.Function):
                 g = gl
         if g is None:
             return None, None, None
-        g = g / torch.sqrt(torch.tensor(D).float())
-        d1 = torch.einsum('ajkh,aijh->aijk', g, f2)
-        d2 = torch.einsum('ajkh,aijk->aijh', g, f1)
+        g = g.to(f1.dtype).contiguous()
+        d1, d2 = torch.empty_like(f1), torch.empty_like(f2)
+        with torch.cuda.device(f1.device):
+            rc = _lib.lib.gpsg_corr_build_backward(_dev(f1), _stream(f1), _DT[f1.dtype], B, D, H, W1, W2,
+                                                   C.c_void_p(f1.data_ptr()), C.c_void_p(f2.data_ptr()),
+                                                   C.c_void_p(g.data_ptr()), C.c_void_p(d1.data_ptr()),
+                                                   C.c_void_p(d2.data_ptr()))
+        _lib.check(rc, "gpsg_corr_build_backward")
         return d1, d2, None
 
 

@@ -336,4 +336,87 @@ int launch_corr_lookup_bwd(int dtype, int B, int H, int W1, void* const* gvols, 
     return GPSG_OK;
 }
 
+// =====================================================================================================
+// Backward of the volume build w.r.t. the feature maps:  dF1[b,d,h,x] = sum_y g[b,h,x,y] F2[b,d,h,y] / sqrt(D),
+// dF2[b,d,h,y] = sum_x g[b,h,x,y] F1[b,d,h,x] / sqrt(D), with g = d(loss)/d(level-0 volume) (the pooled levels'
+// gradients already folded in).  Per (b,h) these are the GEMMs  F2 (D x W2) * g^T  and  F1 (D x W1) * g.
+// One templated smem-tiled FFMA kernel: C[M=D x N] = A[D x K] * Bm[K x N], 64 x 128 output tile, K chunks of 32;
+// TRANS_B selects whether Bm(k,n) = g[n*ldg + k] (dF1: k=y, n=x) or g[k*ldg + n] (dF2: k=x, n=y).
+// =====================================================================================================
+template <typename T, bool TRANS_B>
+__global__ void __launch_bounds__(256) corr_build_bwd_kernel(int D, int H, int N, int K, const T* __restrict__ fmap,
+                                                             const T* __restrict__ g, T* __restrict__ dfmap, float div) {
+    constexpr int BM = 64, BN = 128, BK = 32;
+    __shared__ float As[BK][BM];
+    __shared__ float Bs[BK][BN];
+    const int n_tiles = (N + BN - 1) / BN;
+    const int m_tile = blockIdx.x / n_tiles, n_tile = blockIdx.x % n_tiles;
+    const int b = blockIdx.y / H, h = blockIdx.y % H;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;       // tx: 8 consecutive n, ty: 4 consecutive d
+    const size_t planeK = (size_t)H * K, planeN = (size_t)H * N;
+    const T* A = fmap + (size_t)b * D * planeK + (size_t)h * K;   // A(d,k) = fmap[b,d,h,k]
+    const size_t ldg = TRANS_B ? (size_t)K : (size_t)N;           // row length of g[b,h] (x-major: W1 rows of W2)
+    const T* G = g + ((size_t)b * H + h) * (TRANS_B ? (size_t)N * K : (size_t)K * N);
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const int d0 = m_tile * BM, n0 = n_tile * BN;
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        for (int e = threadIdx.x; e < BK * BM; e += 256) {       // A tile: BM rows (d) x BK (k), k contiguous in memory
+            const int kk = e % BK, dd = e / BK;
+            As[kk][dd] = (d0 + dd < D && k0 + kk < K) ? ld_f<T>(A + (size_t)(d0 + dd) * planeK + k0 + kk) : 0.f;
+        }
+        for (int e = threadIdx.x; e < BK * BN; e += 256) {
+            int kk, nn;
+            if (TRANS_B) { kk = e % BK; nn = e / BK; } else { nn = e % BN; kk = e / BN; }   // contiguous index fastest
+            float v = 0.f;
+            if (n0 + nn < N && k0 + kk < K)
+                v = TRANS_B ? ld_f<T>(G + (size_t)(n0 + nn) * ldg + k0 + kk) : ld_f<T>(G + (size_t)(k0 + kk) * ldg + n0 + nn);
+            Bs[kk][nn] = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int d = d0 + ty * 4 + i;
+        if (d >= D) break;
+        T* o = dfmap + (size_t)b * D * planeN + (size_t)d * planeN + (size_t)h * N + n0 + tx * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (n0 + tx * 8 + j < N) st_f<T>(o + j, acc[i][j] / div);
+    }
+}
+
+int launch_corr_build_bwd(int dtype, int B, int D, int H, int W1, int W2, const void* f1, const void* f2, const void* g,
+                          void* df1, void* df2, cudaStream_t stream) {
+    if ((int64_t)B * D * H * W1 * W2 == 0) return GPSG_OK;
+    const float div = sqrtf((float)D);
+    const int mt = (D + 63) / 64;
+    dim3 g1(mt * ((W1 + 127) / 128), B * H), g2(mt * ((W2 + 127) / 128), B * H);
+    if (dtype == 0) {
+        corr_build_bwd_kernel<float, true><<<g1, 256, 0, stream>>>(D, H, W1, W2, (const float*)f2, (const float*)g, (float*)df1, div);
+        corr_build_bwd_kernel<float, false><<<g2, 256, 0, stream>>>(D, H, W2, W1, (const float*)f1, (const float*)g, (float*)df2, div);
+    } else {
+        corr_build_bwd_kernel<__half, true><<<g1, 256, 0, stream>>>(D, H, W1, W2, (const __half*)f2, (const __half*)g, (__half*)df1, div);
+        corr_build_bwd_kernel<__half, false><<<g2, 256, 0, stream>>>(D, H, W2, W1, (const __half*)f1, (const __half*)g, (__half*)df2, div);
+    }
+    GPSG_LAUNCH_CHECK();
+    return GPSG_OK;
+}
+
 }  // namespace gpsg

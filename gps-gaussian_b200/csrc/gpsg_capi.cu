@@ -549,6 +549,17 @@ int gpsg_corr_build_pyramid(int device, void* stream_, int dtype, int B, int D, 
                              levels > 2 ? vols[2] : nullptr, levels > 3 ? vols[3] : nullptr, levels, (cudaStream_t)stream_);
 }
 
+int gpsg_corr_build_backward(int device, void* stream_, int dtype, int B, int D, int H, int W1, int W2, const void* fmap1,
+                             const void* fmap2, const void* grad_vol0, void* dfmap1, void* dfmap2) {
+    GPSG_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp32) or 1 (fp16)");
+    GPSG_REQUIRE(B >= 0 && D > 0 && H >= 0 && W1 >= 0 && W2 >= 0, "bad shape");
+    if ((int64_t)B * H * W1 * W2 == 0) return GPSG_OK;
+    GPSG_REQUIRE(fmap1 && fmap2 && grad_vol0 && dfmap1 && dfmap2, "NULL pointer");
+    GPSG_CUDA(cudaSetDevice(device));
+    StageTimer t(ST_CORR_BUILD, (cudaStream_t)stream_, 2);
+    return launch_corr_build_bwd(dtype, B, D, H, W1, W2, fmap1, fmap2, grad_vol0, dfmap1, dfmap2, (cudaStream_t)stream_);
+}
+
 int gpsg_corr_lookup_pyramid_forward(int device, void* stream_, int dtype, int B, int H, int W1, const void* const* vols,
                                      const int32_t* widths, int levels, const float* coords, int64_t coords_sb, int radius,
                                      void* out) {

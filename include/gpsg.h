@@ -175,6 +175,10 @@ GPSG_API int gpsg_corr_sampler_backward(int device, void* stream, int dtype, int
  *   (coords: channel 0 of [B,C,H,W1] fp32, level l uses coords / 2^l).  _backward: grad_out -> grad_vol[l] (fully written). */
 GPSG_API int gpsg_corr_build_pyramid(int device, void* stream, int dtype, int B, int D, int H, int W1, int W2,
                                      const void* fmap1, const void* fmap2, void* const* vols, int levels);
+/* backward of the build w.r.t. the feature maps: grad_vol0[B,H,W1,W2] (pooled levels already folded in) -> d fmap1, d fmap2 */
+GPSG_API int gpsg_corr_build_backward(int device, void* stream, int dtype, int B, int D, int H, int W1, int W2,
+                                      const void* fmap1, const void* fmap2, const void* grad_vol0, void* dfmap1,
+                                      void* dfmap2);
 GPSG_API int gpsg_corr_lookup_pyramid_forward(int device, void* stream, int dtype, int B, int H, int W1,
                                               const void* const* vols, const int32_t* widths, int levels,
                                               const float* coords, int64_t coords_sb, int radius, void* out);
