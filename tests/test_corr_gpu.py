@@ -146,3 +146,26 @@ def test_fused_pyramid_build_vs_oracle(dtype, tol):
         got = blk.corr_pyramid[i]
         assert got.shape == (2, 6, 128, 1, 128 >> i) and got.dtype == dtype
         assert np.abs(got.squeeze(3).float().cpu().numpy() - pyr[i]).max() < tol * max(1.0, np.abs(pyr[i]).max())
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.float16, 4e-3)])
+@pytest.mark.parametrize("shape", [(1, 192, 4, 128, 128), (2, 70, 3, 33, 150), (1, 5, 1, 1, 1)])
+def test_build_backward_kernel_vs_fp64_contractions(dtype, tol, shape):
+    """gpsg_corr_build_backward: dF1 = F2 g^T / sqrt(D), dF2 = F1 g / sqrt(D) vs fp64 einsum (W1 != W2, ragged tiles)."""
+    import ctypes as C
+    from gps_gaussian_b200 import _lib
+    B, D, H, W1, W2 = shape
+    gen = torch.Generator("cuda").manual_seed(11)
+    f1 = torch.randn(B, D, H, W1, device="cuda", generator=gen).to(dtype)
+    f2 = torch.randn(B, D, H, W2, device="cuda", generator=gen).to(dtype)
+    g = torch.randn(B, H, W1, W2, device="cuda", generator=gen).to(dtype)
+    d1, d2 = torch.full_like(f1, float("nan")), torch.full_like(f2, float("nan"))
+    p = lambda t: C.c_void_p(t.data_ptr())
+    rc = _lib.lib.gpsg_corr_build_backward(0, C.c_void_p(torch.cuda.current_stream().cuda_stream),
+                                           0 if dtype == torch.float32 else 1, B, D, H, W1, W2, p(f1), p(f2), p(g), p(d1), p(d2))
+    _lib.check(rc, "gpsg_corr_build_backward")
+    r1 = torch.einsum("bhxy,bdhy->bdhx", g.double(), f2.double()) / D ** 0.5
+    r2 = torch.einsum("bhxy,bdhx->bdhy", g.double(), f1.double()) / D ** 0.5
+    for got, ref in ((d1, r1), (d2, r2)):
+        assert torch.isfinite(got).all()
+        assert float((got.double() - ref).abs().max()) < tol * max(1.0, float(ref.abs().max()))
