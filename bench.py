@@ -382,7 +382,40 @@ def main():
             flow2xyz(udata)
         torch.cuda.synchronize()
         p2r["fused_unproject_both_views_ms"] = (time.perf_counter() - t0) * 1e3 / 50
-    del scm, pdata, udata
+    # the loop around it: test_view_interp.py:39-47 sweeps novel cameras over ONE pair -- cached Gaussians + batched
+    # closed-form calibration + sync-free renders (novel_views.NovelViewRenderer) vs per-view get_novel_calib + pts2render
+    from types import SimpleNamespace
+    from gps_gaussian_b200.novel_calib import get_novel_calib
+    from gps_gaussian_b200.novel_views import NovelViewRenderer
+    for name, vw in zip(("lmain", "rmain"), scm["views"]):
+        pdata[name]["intr"] = torch.tensor(vw["K"].astype(np.float32))[None].to(dev)
+        pdata[name]["extr"] = torch.tensor(vw["E"].astype(np.float32))[None].to(dev)
+    opt = SimpleNamespace(use_hr_img=False, znear=_synth.ZNEAR, zfar=_synth.ZFAR, trans=[0.0, 0.0, 0.0], scale=1.0)
+    ratios = [(i + 0.5) / 32 for i in range(32)]
+    sweep = {"views_per_sweep": len(ratios)}
+    with torch.no_grad():
+        for mode in ("compact", "maps"):
+            t0 = time.perf_counter()
+            nvr = NovelViewRenderer(pdata, opt, [0.0, 0.0, 0.0], streams=args.streams, mode=mode)
+            torch.cuda.synchronize()
+            sweep[mode + "_build_ms"] = (time.perf_counter() - t0) * 1e3
+            buf = torch.empty((1, len(ratios), 3, RES, RES), device=dev)
+            nvr.render(ratios, out=buf)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                nvr.render(ratios, out=buf)
+            torch.cuda.synchronize()
+            sweep[mode + "_views_per_s"] = 5 * len(ratios) / (time.perf_counter() - t0)
+            del nvr
+        t0 = time.perf_counter()
+        for r in ratios:
+            pts2render(get_novel_calib(pdata, opt, ratio=r), [0.0, 0.0, 0.0])
+        torch.cuda.synchronize()
+        sweep["per_view_calib_plus_pts2render_views_per_s"] = len(ratios) / (time.perf_counter() - t0)
+        sweep["max_abs_diff_last_view"] = float((buf[0, -1] - pdata["novel_view"]["img_pred"][0]).abs().max())
+    p2r["novel_view_sweep"] = sweep
+    del scm, pdata, udata, buf
 
     # ---- optional: forward+backward (training replay of the rasterizer) ----
     train = None

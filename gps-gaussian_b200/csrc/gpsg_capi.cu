@@ -334,27 +334,20 @@ const uint32_t* gpsg_raster_status_ptr(const void* image_buffer, int W, int H) {
     return ImageState::carve(const_cast<void*>(image_buffer), W, H).totals;
 }
 
-int gpsg_rasterize_forward_planned(const GpsgRasterSettings* s, int device, void* stream_, int P, const float* means3D,
-                                   const float* colors_precomp, const float* opacities, const float* scales,
-                                   const float* rotations, const float* cov3D_precomp, float* out_color, int32_t* radii,
-                                   void* geom_buffer, void* binning_buffer, int64_t capacity_pairs, void* image_buffer,
-                                   uint32_t* status_host) {
+static int forward_planned_common(const GpsgRasterSettings* s, int device, cudaStream_t stream, int P, const GaussianSrc& src,
+                                  float* out_color, int32_t* radii, void* geom_buffer, void* binning_buffer,
+                                  int64_t capacity_pairs, void* image_buffer, uint32_t* status_host) {
     GPSG_REQUIRE(s != nullptr, "settings is NULL");
     GPSG_REQUIRE(P > 0, "planned forward needs P > 0");
     GPSG_REQUIRE(s->image_width > 0 && s->image_height > 0, "image size must be positive");
-    GPSG_REQUIRE(means3D && colors_precomp && opacities && out_color && radii, "a required pointer is NULL");
-    GPSG_REQUIRE(((scales != nullptr && rotations != nullptr) != (cov3D_precomp != nullptr)),
-                 "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+    GPSG_REQUIRE(out_color && radii, "out_color / radii is NULL");
     GPSG_REQUIRE(geom_buffer && binning_buffer && image_buffer && capacity_pairs > 0 && capacity_pairs < (1ll << 31),
                  "planned forward: buffers / capacity missing");
-    cudaStream_t stream = (cudaStream_t)stream_;
     GPSG_CUDA(cudaSetDevice(device));
     const Camera cam = make_camera(*s);
     GeomState g = GeomState::carve(geom_buffer, P, 0);
     ImageState im = ImageState::carve(image_buffer, cam.W, cam.H);
     BinningState b = BinningState::carve(binning_buffer, (size_t)capacity_pairs, 0);
-    const GaussianSrc src = aos_src(means3D, cov3D_precomp ? nullptr : scales, cov3D_precomp ? nullptr : rotations, opacities,
-                                    colors_precomp, cov3D_precomp);
     int rc = GPSG_OK;
     GPSG_CUDA(cudaMemsetAsync(im.tile_count, 0, (size_t)((char*)(im.totals + 64) - (char*)im.tile_count), stream));
     { StageTimer t(ST_PREPROCESS, stream, 1); rc = launch_preprocess(cam, P, src, radii, g, im, (uint32_t)capacity_pairs, stream); }
@@ -366,6 +359,32 @@ int gpsg_rasterize_forward_planned(const GpsgRasterSettings* s, int device, void
     if (rc) return rc;
     { StageTimer t(ST_RENDER_FWD, stream, 1); rc = launch_render_forward(cam, b, im, out_color, stream); }
     return rc;
+}
+
+int gpsg_rasterize_forward_planned(const GpsgRasterSettings* s, int device, void* stream_, int P, const float* means3D,
+                                   const float* colors_precomp, const float* opacities, const float* scales,
+                                   const float* rotations, const float* cov3D_precomp, float* out_color, int32_t* radii,
+                                   void* geom_buffer, void* binning_buffer, int64_t capacity_pairs, void* image_buffer,
+                                   uint32_t* status_host) {
+    GPSG_REQUIRE(means3D && colors_precomp && opacities, "a required pointer is NULL");
+    GPSG_REQUIRE(((scales != nullptr && rotations != nullptr) != (cov3D_precomp != nullptr)),
+                 "Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+    return forward_planned_common(s, device, (cudaStream_t)stream_, P,
+                                  aos_src(means3D, cov3D_precomp ? nullptr : scales, cov3D_precomp ? nullptr : rotations,
+                                          opacities, colors_precomp, cov3D_precomp),
+                                  out_color, radii, geom_buffer, binning_buffer, capacity_pairs, image_buffer, status_host);
+}
+
+int gpsg_rasterize_forward_maps_planned(const GpsgRasterSettings* s, int device, void* stream_, int pixels_per_view,
+                                        const uint8_t* const* valid, const float* const* xyz, const float* const* img,
+                                        const float* const* rot, const float* const* scale, const float* const* opacity,
+                                        float* out_color, int32_t* radii, void* geom_buffer, void* binning_buffer,
+                                        int64_t capacity_pairs, void* image_buffer, uint32_t* status_host) {
+    int rc = check_maps(pixels_per_view, valid, xyz, img, rot, scale, opacity);
+    if (rc) return rc;
+    return forward_planned_common(s, device, (cudaStream_t)stream_, 2 * pixels_per_view,
+                                  maps_src(pixels_per_view, valid, xyz, img, rot, scale, opacity), out_color, radii,
+                                  geom_buffer, binning_buffer, capacity_pairs, image_buffer, status_host);
 }
 
 size_t gpsg_rasterize_backward_workspace_bytes(int P) {

@@ -35,19 +35,45 @@ class PlannedRasterizer:
         self.capacity = int(cap)
         self.binning = torch.empty(int(_lib.lib.gpsg_raster_binning_bytes(self.capacity)), dtype=torch.uint8, device=self.dev)
 
-    def forward(self, settings, means3D, colors, opacity, scales, rots, cov3D_precomp=None):
-        """Enqueue one forward on the current stream.  Inputs: contiguous fp32 CUDA tensors; `settings`: a
+    def forward(self, settings, means3D, colors, opacity, scales, rots, cov3D_precomp=None, out=None, status_host=None):
+        """Enqueue one forward on the current stream (P = means3D.shape[0] may be smaller than the P the scratch was
+        sized for; `out` / `status_host` redirect the image / deferred status words, as in forward_maps).  Inputs: contiguous fp32 CUDA tensors; `settings`: a
         `_lib.RasterSettings` (see introspect.make_settings) or a synth scene dict.  Returns self.color (valid once the
         stream has run AND ok() holds)."""
         if isinstance(settings, dict):
             settings = make_settings(settings)
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        P = int(means3D.shape[0])
+        if P > self.P:
+            raise ValueError(f"PlannedRasterizer scratch holds P<={self.P}, got {P}")
+        color = self.color if out is None else out
         rc = _lib.lib.gpsg_rasterize_forward_planned(
-            C.byref(settings), self.idx, C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream), self.P, p(means3D),
-            p(colors), p(opacity), p(scales), p(rots), p(cov3D_precomp), p(self.color), p(self.radii), p(self.geom),
-            p(self.binning), self.capacity, p(self.image), C.c_void_p(self.status_host.data_ptr()))
+            C.byref(settings), self.idx, C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream), P, p(means3D),
+            p(colors), p(opacity), p(scales), p(rots), p(cov3D_precomp), p(color), p(self.radii), p(self.geom),
+            p(self.binning), self.capacity, p(self.image),
+            C.c_void_p((self.status_host if status_host is None else status_host).data_ptr()))
         _lib.check(rc, "gpsg_rasterize_forward_planned")
-        return self.color
+        return color
+
+    def forward_maps(self, settings, valid, xyz, img, rot, scale, opacity, out=None, status_host=None):
+        """Same, reading the two source views' pixel-aligned maps in place (`gpsg_rasterize_forward_maps_planned`):
+        each argument is a pair (lmain, rmain) of contiguous CUDA tensors -- valid uint8/bool [S2], xyz [S2,3], img
+        [3,S2] in [-1,1], rot [4,S2], scale [3,S2], opacity [1,S2]; self.P must be 2*S2.  `out` optionally redirects
+        the image to another [3,H,W] tensor (e.g. a slice of a batch); `status_host` optionally redirects the deferred
+        status words to another pinned int32[>=3] tensor (one per in-flight job)."""
+        S2 = int(valid[0].numel())
+        if 2 * S2 != self.P:
+            raise ValueError(f"PlannedRasterizer built for P={self.P}, maps hold 2*{S2} candidates")
+        pp = lambda ts: (C.c_void_p * 2)(*[t.data_ptr() for t in ts])
+        color = self.color if out is None else out
+        rc = _lib.lib.gpsg_rasterize_forward_maps_planned(
+            C.byref(settings), self.idx, C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream), S2, pp(valid), pp(xyz),
+            pp(img), pp(rot), pp(scale), pp(opacity), C.c_void_p(color.data_ptr()), C.c_void_p(self.radii.data_ptr()),
+            C.c_void_p(self.geom.data_ptr()), C.c_void_p(self.binning.data_ptr()), self.capacity,
+            C.c_void_p(self.image.data_ptr()),
+            C.c_void_p((self.status_host if status_host is None else status_host).data_ptr()))
+        _lib.check(rc, "gpsg_rasterize_forward_maps_planned")
+        return color
 
     # ---- deferred status (call after a synchronisation that covers the forward) ----
     def status(self):

@@ -120,6 +120,15 @@ GPSG_API int gpsg_rasterize_forward_maps(const GpsgRasterSettings* settings, int
                                          float* out_color, int32_t* radii, gpsg_alloc_fn geom_alloc, void* geom_user,
                                          gpsg_alloc_fn binning_alloc, void* binning_user, gpsg_alloc_fn image_alloc,
                                          void* image_user, int32_t* num_rendered);
+/* sync-free form of gpsg_rasterize_forward_maps (same contract as gpsg_rasterize_forward_planned; geom buffer sized for
+ * P = 2*pixels_per_view): the serving loop of test_view_interp.py:39-47 renders many novel cameras from ONE pair's
+ * cached maps without gathering them and without a host sync. */
+GPSG_API int gpsg_rasterize_forward_maps_planned(const GpsgRasterSettings* settings, int device, void* stream,
+                                                 int pixels_per_view, const uint8_t* const* valid, const float* const* xyz,
+                                                 const float* const* img, const float* const* rot,
+                                                 const float* const* scale, const float* const* opacity, float* out_color,
+                                                 int32_t* radii, void* geom_buffer, void* binning_buffer,
+                                                 int64_t capacity_pairs, void* image_buffer, uint32_t* status_host);
 GPSG_API size_t gpsg_rasterize_backward_maps_workspace_bytes(int pixels_per_view);
 GPSG_API int gpsg_rasterize_backward_maps(const GpsgRasterSettings* settings, int device, void* stream, int pixels_per_view,
                                           int32_t num_rendered, const uint8_t* const* valid, const float* const* xyz,
