@@ -440,6 +440,34 @@ def main():
         train = {"value": V * args.steps / (tms * 1e-3), "unit": "fwd+bwd views/s (1 GPU)",
                  "stages_ms": {k: v["ms"] / max(v["calls"], 1) for k, v in tprof.items() if v["calls"]},
                  "render_backward_gbps": b_cbwd / (rb["ms"] / max(rb["calls"], 1) * 1e-3) / 1e9 if rb["calls"] else None}
+        # the loss between them (train_stage2.py:70-72): fused L1+SSIM kernels vs the op-by-op torch data flow of lib/loss.py
+        import torch.nn.functional as F
+        from gps_gaussian_b200.loss import fused_l1_ssim
+
+        def torch_ops_loss(x, y):
+            gw = torch.tensor([np.exp(-(i - 5) ** 2 / 4.5) for i in range(11)], dtype=torch.float32, device=dev)
+            gw = gw / gw.sum()
+            win = (gw[:, None] * gw[None, :]).expand(3, 1, 11, 11).contiguous()
+            cv = lambda t: F.conv2d(t, win, padding=5, groups=3)
+            m1, m2 = cv(x), cv(y)
+            s1, s2, s12 = cv(x * x) - m1 * m1, cv(y * y) - m2 * m2, cv(x * y) - m1 * m2
+            sm = ((2 * m1 * m2 + 1e-4) * (2 * s12 + 9e-4)) / ((m1 * m1 + m2 * m2 + 1e-4) * (s1 + s2 + 9e-4))
+            return 0.8 * (x - y).abs().mean() + 0.2 * (1.0 - sm.mean())
+
+        gt_img = calls[1].color.detach().clone()[None]
+        lt = {}
+        for nm, fn in (("fused_fwd_bwd_ms", fused_l1_ssim), ("torch_ops_fwd_bwd_ms", torch_ops_loss)):
+            xi = calls[0].color.detach().clone()[None].requires_grad_(True)
+            for _ in range(3):
+                fn(xi, gt_img).backward()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                fn(xi, gt_img).backward()
+            e1.record()
+            torch.cuda.synchronize()
+            lt[nm] = e0.elapsed_time(e1) / 20
+        train["l1_ssim_loss_1024sq"] = lt
 
     if rank != 0:
         if world > 1:

@@ -29,6 +29,7 @@ SOURCES = {
     "corr.cu": [],
     "sh.cu": [],
     "unproject.cu": [],
+    "loss.cu": [],
 }
 
 

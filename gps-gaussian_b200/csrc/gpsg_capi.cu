@@ -626,6 +626,26 @@ int gpsg_unproject_backward(int device, void* stream_, int B, int S, const float
                                 dL_ddepth, dL_dflow, (cudaStream_t)stream_);
 }
 
+size_t gpsg_l1_ssim_workspace_bytes(int planes, int H, int W) {
+    return (planes > 0 && H > 0 && W > 0) ? l1_ssim_workspace_bytes(planes, H, W) : 256;
+}
+
+int gpsg_l1_ssim_forward(int device, void* stream_, int planes, int H, int W, const float* img, const float* gt, float w_l1,
+                         float w_ssim, float* out3, float* dmaps, void* workspace) {
+    GPSG_REQUIRE(planes > 0 && H > 0 && W > 0, "l1_ssim: empty image");
+    GPSG_REQUIRE(img && gt && out3 && workspace, "NULL pointer");
+    GPSG_CUDA(cudaSetDevice(device));
+    return launch_l1_ssim_fwd(planes, H, W, img, gt, w_l1, w_ssim, out3, dmaps, workspace, (cudaStream_t)stream_);
+}
+
+int gpsg_l1_ssim_backward(int device, void* stream_, int planes, int H, int W, const float* img, const float* gt,
+                          const float* dmaps, float w_l1, float w_ssim, const float* grad_loss, float* dimg) {
+    GPSG_REQUIRE(planes > 0 && H > 0 && W > 0, "l1_ssim: empty image");
+    GPSG_REQUIRE(img && gt && dmaps && dimg, "NULL pointer");
+    GPSG_CUDA(cudaSetDevice(device));
+    return launch_l1_ssim_bwd(planes, H, W, img, gt, dmaps, w_l1, w_ssim, grad_loss, dimg, (cudaStream_t)stream_);
+}
+
 int gpsg_profile_enable(int on) {
     g_prof.on = on != 0;
     return GPSG_OK;

@@ -190,6 +190,11 @@ int launch_corr_lookup_fwd(int dtype, int B, int H, int W1, const void* const* v
 int launch_corr_lookup_bwd(int dtype, int B, int H, int W1, void* const* gvols, const int* widths, int levels,
                            const float* coords, int64_t csb, int r, const void* gout, cudaStream_t stream);
 
+size_t l1_ssim_workspace_bytes(int planes, int H, int W);
+int launch_l1_ssim_fwd(int planes, int H, int W, const float* img, const float* gt, float w_l1, float w_ssim, float* out3,
+                       float* dmaps, void* workspace, cudaStream_t stream);
+int launch_l1_ssim_bwd(int planes, int H, int W, const float* img, const float* gt, const float* dmaps, float w_l1,
+                       float w_ssim, const float* grad_loss, float* dimg, cudaStream_t stream);
 
 // ---- optional per-stage timing (bench.py); see gpsg_profile_* in gpsg.h ---------------------
 enum Stage { ST_PREPROCESS = 0, ST_SCAN, ST_DUPLICATE, ST_SORT, ST_GATHER, ST_TILE_SCAN, ST_SCATTER, ST_TILE_SORT, ST_RENDER_FWD, ST_RENDER_BWD,

@@ -207,6 +207,18 @@ GPSG_API int gpsg_unproject_backward(int device, void* stream, int B, int S, con
                                      const float* ref_intr, const float* Tf_x, const float* dL_dxyz,
                                      const float* dL_ddepth, float* dL_dflow);
 
+/* ---- fused photometric loss on the rendered image -----------------------------------------------
+ * replaces  0.8 * l1_loss(img, gt) + 0.2 * (1 - ssim(img, gt))  (train_stage2.py:70-72; lib/loss.py:35-72: 11x11 Gaussian
+ * window sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2, means over all planes*H*W elements) and its autograd.
+ * img, gt: [planes, H, W] fp32 (planes = B*C).  out3 (device float[3]) = { w_l1*L1 + w_ssim*(1-SSIM), L1, SSIM }.
+ * dmaps (device float[3*planes*H*W], NULL when no gradient is needed) keeps the per-pixel SSIM partials for the backward,
+ * which writes dimg = grad_loss * d(out3[0])/d(img); grad_loss is a DEVICE pointer to one float (NULL = 1). */
+GPSG_API size_t gpsg_l1_ssim_workspace_bytes(int planes, int H, int W);
+GPSG_API int gpsg_l1_ssim_forward(int device, void* stream, int planes, int H, int W, const float* img, const float* gt,
+                                  float w_l1, float w_ssim, float* out3, float* dmaps, void* workspace);
+GPSG_API int gpsg_l1_ssim_backward(int device, void* stream, int planes, int H, int W, const float* img, const float* gt,
+                                   const float* dmaps, float w_l1, float w_ssim, const float* grad_loss, float* dimg);
+
 /* ---- measurement hooks (used by bench.py; off by default) -----------------------------------
  * When enabled, every stage of the forward/backward is bracketed by CUDA events on the launching stream.
  * gpsg_profile_read() synchronises, then returns for stage i: total_ms[i] (summed over the calls since the last
