@@ -178,6 +178,55 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def _corr_section(dev, hbm_peak_gbs):
+    """Volume + pyramid build (fp16 tcgen05 kernel / fp16 + fp32 FFMA kernels) and the fused 4-level lookup, CUDA-event timed."""
+    import torch
+    from gps_gaussian_b200.corr import CorrBlockFast1D
+    B, D, H, W = 2, 192, 128, 128
+    gen = torch.Generator(device=dev).manual_seed(1314)
+    f32 = [torch.randn(B, D, H, W, device=dev, generator=gen) for _ in range(2)]
+    f16 = [t.half() for t in f32]
+    coords = torch.stack(torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")[::-1])[None]
+    coords = (coords.float() + 6.0 * torch.randn(B, 2, H, W, device=dev, generator=gen)).contiguous()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, n=50):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    out = {"shape": [B, D, H, W]}
+    alg = lambda s: 2 * B * D * H * W * s + 1.875 * B * H * W * W * s          # SURVEY 8d: features in, volume + pyramid out
+    with torch.no_grad():
+        out["build_fp16_tcgen05_ms"] = timed(lambda: CorrBlockFast1D(f16[0], f16[1]))
+        os.environ["GPSG_CORR_BUILD"] = "ffma"
+        out["build_fp16_ffma_ms"] = timed(lambda: CorrBlockFast1D(f16[0], f16[1]))
+        os.environ.pop("GPSG_CORR_BUILD")
+        out["build_fp32_ffma_ms"] = timed(lambda: CorrBlockFast1D(f32[0], f32[1]))
+        blk = CorrBlockFast1D(f16[0], f16[1])
+        out["lookup_4level_fp16_ms"] = timed(lambda: blk(coords))
+        # library data flow of the reference (core/corr.py:53-61 + :36-42) for comparison
+        def ref_build():
+            c = torch.einsum('aijk,aijh->ajkh', f16[0], f16[1]).reshape(B, H, W, 1, W) / torch.sqrt(torch.tensor(D).float())
+            c = c.reshape(B * H * W, 1, 1, W)
+            pyr = [c]
+            for _ in range(3):
+                c = torch.nn.functional.avg_pool2d(c, [1, 2], stride=[1, 2])
+                pyr.append(c)
+            return pyr
+        out["build_fp16_torch_ops_ms"] = timed(ref_build)
+    out["build_fp16_tcgen05_gbps"] = alg(2) / (out["build_fp16_tcgen05_ms"] * 1e-3) / 1e9
+    out["build_fp16_tcgen05_hbm_frac"] = out["build_fp16_tcgen05_gbps"] / hbm_peak_gbs
+    out["note"] = "wall of the Python call (allocation of the 4 level tensors + 1 launch), CUDA events, back-to-back"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -492,6 +541,13 @@ def main():
         except Exception:
             traffic = None
 
+    # ---- the other half of the path: RAFT-Stereo 1-D correlation at the C2 input size (fmaps [2,192,128,128]) ----
+    corr = None
+    try:
+        corr = _corr_section(dev, peak)
+    except Exception as exc:                                   # never lose the headline line to an auxiliary measurement
+        corr = {"error": repr(exc)}
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         vps, threads, dt = _cpu_oracle_views_per_sec(scenes[0], 8)
@@ -515,7 +571,7 @@ def main():
                          "kernel_ms_overlapped_timed_region": prof_overlapped["render_forward"]["ms"] / max(prof_overlapped["render_forward"]["calls"], 1),
                          "serial_ms_per_view": serial_ms_per_view,
                          "note": "compositing is FP32/SFU-bound by design (about 130 FLOP/B); see DESIGN.md"},
-            "stages_ms": stages, "value_cuda_graph_replay": graph_value, "pts2render_ms_per_call": p2r,
+            "stages_ms": stages, "value_cuda_graph_replay": graph_value, "pts2render_ms_per_call": p2r, "corr": corr,
             "entry_point": "gpsg_rasterize_forward_planned (sync-free; verified bit-identical to gpsg_rasterize_forward)",
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -27,6 +27,7 @@ SOURCES = {
     "raster_render.cu": [],
     "raster_backward.cu": [],
     "corr.cu": [],
+    "corr_tc.cu": [],
     "sh.cu": [],
     "unproject.cu": [],
     "loss.cu": [],

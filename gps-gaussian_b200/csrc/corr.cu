@@ -4,6 +4,9 @@
 #include <cuda_fp16.h>
 #include "gpsg_internal.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace gpsg {
 
 template <typename T> __device__ __forceinline__ float ld_f(const T* p);
@@ -210,6 +213,12 @@ __global__ void __launch_bounds__(256) corr_build_kernel(int B, int D, int H, in
 int launch_corr_build(int dtype, int B, int D, int H, int W1, int W2, const void* f1, const void* f2, void* v0, void* v1,
                       void* v2, void* v3, int levels, cudaStream_t stream) {
     if ((int64_t)B * H * W1 * W2 == 0) return GPSG_OK;
+    {   // fp16 (stage-2 AMP) volumes go to the tcgen05 kernel (corr_tc.cu) when the shape fits; GPSG_CORR_BUILD=ffma opts out
+        void* lv[4] = {v0, v1, v2, v3};
+        const char* e = getenv("GPSG_CORR_BUILD");
+        if (!(e && strcmp(e, "ffma") == 0) && corr_build_tc_supported(dtype, D, W1, W2, f1, f2, lv, levels))
+            return launch_corr_build_tc(B, D, H, W1, W2, f1, f2, v0, v1, v2, v3, levels, stream);
+    }
     const float div = sqrtf((float)D);   // the reference divides by torch.sqrt(torch.tensor(D).float())
     dim3 grid(((W1 + kCT - 1) / kCT) * ((W2 + kCT - 1) / kCT), B * H);
     if (dtype == 0)

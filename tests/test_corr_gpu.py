@@ -169,3 +169,42 @@ def test_build_backward_kernel_vs_fp64_contractions(dtype, tol, shape):
     for got, ref in ((d1, r1), (d2, r2)):
         assert torch.isfinite(got).all()
         assert float((got.double() - ref).abs().max()) < tol * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("shape", [(2, 192, 6, 128, 128), (1, 64, 3, 152, 48), (1, 32, 2, 264, 128), (1, 256, 2, 64, 64),
+                                   (1, 16, 1, 8, 16)])
+def test_fp16_tcgen05_build_matches_ffma_kernel_and_oracle(shape):
+    """fp16 volumes take the tcgen05/TMEM kernel (corr_tc.cu); GPSG_CORR_BUILD=ffma forces the FFMA kernel.  Both follow the
+    same rounding chain, so every pyramid level agrees to one fp16 ulp of the level's magnitude (different fp32 summation
+    order), and both match the fp64 oracle on the quantised inputs.  Shapes: ragged M tiles (W1 = 152, 264), N < 128."""
+    from gps_gaussian_b200.corr import CorrBlockFast1D
+    B, D, H, W1, W2 = shape
+    gen = torch.Generator("cuda").manual_seed(7)
+    f1 = torch.randn(B, D, H, W1, device="cuda", generator=gen).half()
+    f2 = torch.randn(B, D, H, W2, device="cuda", generator=gen).half()
+    tc = [v.clone() for v in CorrBlockFast1D(f1, f2, num_levels=4, radius=4).corr_pyramid]
+    os.environ["GPSG_CORR_BUILD"] = "ffma"
+    try:
+        ff = [v.clone() for v in CorrBlockFast1D(f1, f2, num_levels=4, radius=4).corr_pyramid]
+    finally:
+        os.environ.pop("GPSG_CORR_BUILD")
+    pyr = CorrOracle("f64").pyramid(f1.float().cpu().numpy(), f2.float().cpu().numpy(), 4)
+    for l in range(4):
+        a, b = tc[l].squeeze(3).float(), ff[l].squeeze(3).float()
+        assert a.shape == (B, H, W1, W2 >> l) and tc[l].dtype == torch.float16
+        scale = max(1.0, float(b.abs().max()))
+        assert float((a - b).abs().max()) <= 2.0 ** -10 * scale * 2, l                  # <= 1 ulp at the top binade
+        assert float(((a - b).abs() > 0).float().mean()) < 0.02, l                     # and almost always bit-identical
+        assert np.abs(a.cpu().numpy() - pyr[l]).max() < 3e-3 * max(1.0, np.abs(pyr[l]).max()), l
+
+
+def test_tcgen05_build_falls_back_for_unsupported_shapes():
+    """D not a multiple of 16, W2 > 128, W2 % 16 != 0 or misaligned views use the FFMA kernel: same results as ever."""
+    from gps_gaussian_b200.corr import CorrBlockFast1D
+    gen = torch.Generator("cuda").manual_seed(8)
+    for (B, D, H, W1, W2) in [(1, 24, 2, 40, 40), (1, 32, 2, 64, 160), (1, 32, 1, 24, 24)]:
+        f1 = torch.randn(B, D, H, W1, device="cuda", generator=gen).half()
+        f2 = torch.randn(B, D, H, W2, device="cuda", generator=gen).half()
+        got = CorrBlockFast1D(f1, f2, num_levels=2, radius=4).corr_pyramid[0].squeeze(3).float()
+        ref = torch.einsum("bdhx,bdhy->bhxy", f1.double(), f2.double()) / D ** 0.5
+        assert float((got.double() - ref).abs().max()) < 3e-3 * max(1.0, float(ref.abs().max()))
