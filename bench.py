@@ -221,6 +221,17 @@ def _corr_section(dev, hbm_peak_gbs):
                 pyr.append(c)
             return pyr
         out["build_fp16_torch_ops_ms"] = timed(ref_build)
+    # backward of the build w.r.t. the feature maps (autograd through _BuildPyramid with a level-0 gradient)
+    fa, fb_ = f16[0].clone().requires_grad_(True), f16[1].clone().requires_grad_(True)
+    gvol = torch.randn(B, H, W, W, device=dev, generator=gen).half()
+
+    def bwd():
+        v0 = CorrBlockFast1D.corr(fa, fb_).squeeze(3)
+        torch.autograd.grad(v0, (fa, fb_), gvol)
+    out["build_fwd_bwd_fp16_tcgen05_ms"] = timed(bwd, 20)
+    os.environ["GPSG_CORR_BUILD"] = "ffma"
+    out["build_fwd_bwd_fp16_ffma_ms"] = timed(bwd, 20)
+    os.environ.pop("GPSG_CORR_BUILD")
     out["build_fp16_tcgen05_gbps"] = alg(2) / (out["build_fp16_tcgen05_ms"] * 1e-3) / 1e9
     out["build_fp16_tcgen05_hbm_frac"] = out["build_fp16_tcgen05_gbps"] / hbm_peak_gbs
     out["note"] = "wall of the Python call (allocation of the 4 level tensors + 1 launch), CUDA events, back-to-back"

@@ -59,7 +59,13 @@ class _BuildPyramid(torch.autograd.Function):
         f1, f2 = fmap1.detach().contiguous(), fmap2.detach().contiguous()
         B, D, H, W1 = f1.shape
         W2 = f2.shape[3]
-        vols = [torch.empty((B, H, W1, W2 >> l), dtype=f1.dtype, device=f1.device) for l in range(levels)]
+        # one allocation for the whole pyramid (each level starts on a 16-byte boundary), carved into per-level views
+        sizes = [B * H * W1 * (W2 >> l) for l in range(levels)]
+        offs = [0]
+        for n in sizes[:-1]:
+            offs.append(offs[-1] + ((n + 7) & ~7))
+        buf = torch.empty(offs[-1] + sizes[-1], dtype=f1.dtype, device=f1.device)
+        vols = [buf[o:o + n].view(B, H, W1, W2 >> l) for l, (o, n) in enumerate(zip(offs, sizes))]
         ptrs = (C.c_void_p * 4)(*[v.data_ptr() if v.numel() else None for v in vols] + [None] * (4 - levels))
         with torch.cuda.device(f1.device):
             rc = _lib.lib.gpsg_corr_build_pyramid(_dev(f1), _stream(f1), _DT[f1.dtype], B, D, H, W1, W2,
@@ -151,7 +157,7 @@ class CorrBlockFast1D:
         self.corr_pyramid = [v.unsqueeze(3) for v in self._vols]
 
     def __call__(self, coords):
-        return _LookupPyramid.apply(coords[:, [0]], self.radius, *self._vols)
+        return _LookupPyramid.apply(coords[:, :1], self.radius, *self._vols)      # x channel as a view (reference copies it)
 
     @staticmethod
     def corr(fmap1, fmap2):

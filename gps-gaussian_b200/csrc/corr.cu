@@ -414,6 +414,11 @@ __global__ void __launch_bounds__(256) corr_build_bwd_kernel(int D, int H, int N
 int launch_corr_build_bwd(int dtype, int B, int D, int H, int W1, int W2, const void* f1, const void* f2, const void* g,
                           void* df1, void* df2, cudaStream_t stream) {
     if ((int64_t)B * D * H * W1 * W2 == 0) return GPSG_OK;
+    {   // fp16: tcgen05 kernels (corr_tc.cu) when the shape fits; GPSG_CORR_BUILD=ffma opts out
+        const char* e = getenv("GPSG_CORR_BUILD");
+        if (!(e && strcmp(e, "ffma") == 0) && corr_build_bwd_tc_supported(dtype, D, W1, W2, f1, f2, g, df1, df2))
+            return launch_corr_build_bwd_tc(B, D, H, W1, W2, f1, f2, g, df1, df2, stream);
+    }
     const float div = sqrtf((float)D);
     const int mt = (D + 63) / 64;
     dim3 g1(mt * ((W1 + 127) / 128), B * H), g2(mt * ((W2 + 127) / 128), B * H);

@@ -65,6 +65,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+
+// correctly rounded a / d from r = RN(1/d) with one Newton correction (Markstein): q0 = a r; q = q0 + (a - q0 d) r.
+// Valid here: |a| is an fp16 value (no overflow / underflow in the residual), d = sqrt(D) is a normal fp32 number.
+__device__ __forceinline__ float div_rn_fast(float a, float d, float r) {
+    const float q0 = a * r;
+    return fmaf(fmaf(-q0, d, a), r, q0);
+}
+
 __device__ __forceinline__ float rh(float v) { return __half2float(__float2half_rn(v)); }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     const __half2 h = __halves2half2(__float2half_rn(a), __float2half_rn(b));
@@ -106,22 +117,19 @@ __global__ void __launch_bounds__(kTcThreads) corr_build_tc_kernel(int D, int H,
     const __half* g1 = f1 + (size_t)b * D * plane1 + (size_t)h * W1 + x_base;
     const __half* g2 = f2 + (size_t)b * D * plane2 + (size_t)h * W2;
     const int cl = lane >> 3, dl = lane & 7;
-#pragma unroll 4
+    // cp.async (LDGSTS): every thread puts all of its 16-byte copies in flight before waiting on any of them -- the whole
+    // 2*D*W*2-byte panel pair is outstanding at once (register-staged loads stalled on the scoreboard after 4).
     for (int it = warp; it < KC * 4; it += kTcThreads / 32) {
         const int kc = it >> 2, c = (it & 3) * 4 + cl;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (x_base + c * 8 < W1) v = __ldg(reinterpret_cast<const uint4*>(g1 + (size_t)(kc * 8 + dl) * plane1 + c * 8));
-        *reinterpret_cast<uint4*>(sA + (size_t)kc * 2048 + c * 128 + dl * 16) = v;
+        const bool in = x_base + c * 8 < W1;                      // ragged last M tile: zero-fill (src-size 0)
+        cp_async16(sA + (size_t)kc * 2048 + c * 128 + dl * 16, in ? g1 + (size_t)(kc * 8 + dl) * plane1 + c * 8 : g1, in ? 16u : 0u);
     }
     const int NBg = (NB + 3) >> 2;
-#pragma unroll 4
     for (int it = warp; it < KC * NBg; it += kTcThreads / 32) {
         const int kc = it / NBg, c = (it % NBg) * 4 + cl;
-        if (c < NB) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(g2 + (size_t)(kc * 8 + dl) * plane2 + c * 8));
-            *reinterpret_cast<uint4*>(sB + ((size_t)kc * NB + c) * 128 + dl * 16) = v;
-        }
+        if (c < NB) cp_async16(sB + ((size_t)kc * NB + c) * 128 + dl * 16, g2 + (size_t)(kc * 8 + dl) * plane2 + c * 8, 16u);
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
     tc_fence_before();
     __syncthreads();
@@ -150,6 +158,7 @@ __global__ void __launch_bounds__(kTcThreads) corr_build_tc_kernel(int D, int H,
     const int x = x_base + quad * 32 + lane;
     const size_t row = ((size_t)b * H + h) * W1 + x;
     const int Wl1 = W2 >> 1, Wl2 = W2 >> 2, Wl3 = W2 >> 3;
+    const float rdiv = __frcp_rn(div);
     for (int j = warp >> 2; j < (W2 >> 4); j += 2) {            // 16-column batches, split between the two warp sets
         float acc[16];
         __syncwarp();                                            // tcgen05.ld is .sync.aligned: whole warp, converged
@@ -157,7 +166,7 @@ __global__ void __launch_bounds__(kTcThreads) corr_build_tc_kernel(int D, int H,
         if (x < W1) {
         float q0[16], q1[8], q2[4], q3[2];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) q0[i] = rh(rh(acc[i]) / div);          // einsum result in fp16, then the division in fp16
+        for (int i = 0; i < 16; ++i) q0[i] = rh(div_rn_fast(rh(acc[i]), div, rdiv));   // einsum result in fp16, then the division in fp16
         uint4* o0 = reinterpret_cast<uint4*>(v0 + row * W2 + j * 16);
         o0[0] = make_uint4(pack2(q0[0], q0[1]), pack2(q0[2], q0[3]), pack2(q0[4], q0[5]), pack2(q0[6], q0[7]));
         o0[1] = make_uint4(pack2(q0[8], q0[9]), pack2(q0[10], q0[11]), pack2(q0[12], q0[13]), pack2(q0[14], q0[15]));
@@ -185,6 +194,113 @@ __global__ void __launch_bounds__(kTcThreads) corr_build_tc_kernel(int D, int H,
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
 }
 
+// =====================================================================================================================
+// Backward of the build on the tensor cores (fp16): per (b, h), with g = d(loss)/d(level-0 volume) [W1 x W2],
+//   dF1[d, x] = sum_y g[x, y] F2[d, y] / sqrt(D)        A_MN = false:  M = x, N = d, K = y;  A = g rows (K-major)
+//   dF2[d, y] = sum_x g[x, y] F1[d, x] / sqrt(D)        A_MN = true :  M = y, N = d, K = x;  A = g columns (MN-major)
+// computed transposed (C^T[m, d]) so that M is the 128-wide volume axis and N = D (a multiple of 16 up to 256, which
+// M = 64/128 UMMA shapes accept); B = the other feature map's [D x K] panel, K-contiguous (K-major) in both cases.
+// Shared layout: the same 128-byte core matrices as the forward -- K-major cores hold 8 MN rows x 16 B of 8 K elements.
+// Thread = one TMEM lane = one m; its 16-column batches are 16 different d planes of the output, so a warp stores 64
+// contiguous bytes per (d, 32 m).
+// =====================================================================================================================
+template <bool A_MN>
+__global__ void __launch_bounds__(kTcThreads) corr_build_bwd_tc_kernel(int D, int H, int W1, int W2,
+                                                                       const __half* __restrict__ fmap,
+                                                                       const __half* __restrict__ g,
+                                                                       __half* __restrict__ dfmap, float div,
+                                                                       uint32_t tmem_cols) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y / H, h = blockIdx.y % H;
+    const int Kdim = A_MN ? W1 : W2, Mdim = A_MN ? W2 : W1;
+    const int KC = ((Kdim + 15) & ~15) >> 3;                    // K core groups, K padded to the UMMA K of 16 with zeros
+    const int m_base = blockIdx.x * kTcM;
+    const int NB = D >> 3;
+    uint8_t* sA = smem;                                         // [KC][16 M cores][128 B]
+    uint8_t* sB = smem + (size_t)KC * 2048;                     // [KC][NB N cores][128 B]
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    const __half* gbh = g + ((size_t)b * H + h) * W1 * W2;
+    const int cl = lane >> 3, dl = lane & 7;
+    const int KCg = (KC + 3) >> 2;
+    if (A_MN) {      // g[x][y]: k = x (row), MN cores = chunks of 8 y
+        for (int it = warp; it < KC * 4; it += kTcThreads / 32) {
+            const int kc = it >> 2, c = (it & 3) * 4 + cl;
+            const int x = kc * 8 + dl;
+            const bool in = x < W1 && c * 8 < W2;
+            cp_async16(sA + (size_t)kc * 2048 + c * 128 + dl * 16, in ? gbh + (size_t)x * W2 + c * 8 : gbh, in ? 16u : 0u);
+        }
+    } else {         // g[x][y]: m = x (row), K cores = chunks of 8 y
+        for (int it = warp; it < 16 * KCg; it += kTcThreads / 32) {
+            const int m8 = it / KCg, kc = (it % KCg) * 4 + cl;
+            const int x = m_base + m8 * 8 + dl;
+            if (kc < KC) {
+                const bool in = x < W1 && kc * 8 < W2;
+                cp_async16(sA + (size_t)kc * 2048 + m8 * 128 + dl * 16, in ? gbh + (size_t)x * W2 + kc * 8 : gbh, in ? 16u : 0u);
+            }
+        }
+    }
+    const size_t plane = (size_t)H * Kdim;
+    const __half* fb = fmap + (size_t)b * D * plane + (size_t)h * Kdim;     // F[d][k], k contiguous
+    for (int it = warp; it < NB * KCg; it += kTcThreads / 32) {
+        const int d8 = it / KCg, kc = (it % KCg) * 4 + cl;
+        if (kc < KC) {
+            const bool in = kc * 8 < Kdim;
+            cp_async16(sB + ((size_t)kc * NB + d8) * 128 + dl * 16, in ? fb + (size_t)(d8 * 8 + dl) * plane + kc * 8 : fb,
+                       in ? 16u : 0u);
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (tid == 0) {
+        const uint32_t idesc = (1u << 4) | (A_MN ? (1u << 15) : 0u) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+        const uint32_t lbo_b = (uint32_t)NB * 128u;
+        for (int s = 0; s < (KC >> 1); ++s) {
+            const uint64_t da = umma_desc(a0 + (uint32_t)s * 2u * 2048u, 2048u, 128u);
+            const uint64_t db = umma_desc(b0 + (uint32_t)s * 2u * lbo_b, lbo_b, 128u);
+            umma_f16(tmem, da, db, idesc, s > 0 ? 1u : 0u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar))
+                     : "memory");
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    const int quad = warp & 3;
+    const int m = m_base + quad * 32 + lane;
+    const float rdiv = __frcp_rn(div);
+    __half* o = dfmap + ((size_t)b * D * H + h) * Mdim + m;     // + d * H * Mdim
+    const size_t dplane = (size_t)H * Mdim;
+    for (int j = warp >> 2; j < (D >> 4); j += 2) {
+        float acc[16];
+        __syncwarp();
+        tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(j * 16), acc);
+        if (m < Mdim) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[(size_t)(j * 16 + i) * dplane] = __float2half_rn(div_rn_fast(acc[i], div, rdiv));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
+}
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -209,6 +325,33 @@ int launch_corr_build_tc(int B, int D, int H, int W1, int W2, const void* f1, co
     corr_build_tc_kernel<<<grid, kTcThreads, smem, stream>>>(D, H, W1, W2, (const __half*)f1, (const __half*)f2, (__half*)v0,
                                                             (__half*)v1, (__half*)v2, (__half*)v3, levels,
                                                             sqrtf((float)D));
+    GPSG_LAUNCH_CHECK();
+    return GPSG_OK;
+}
+
+bool corr_build_bwd_tc_supported(int dtype, int D, int W1, int W2, const void* f1, const void* f2, const void* g,
+                                 const void* d1, const void* d2) {
+    if (dtype != 1) return false;
+    if (D < 16 || (D & 15) || D > 256 || W1 < 8 || (W1 & 7) || W2 < 16 || (W2 & 15) || W2 > 128) return false;
+    const size_t kc1 = (size_t)((W2 + 15) & ~15) >> 3, kc2 = (size_t)((W1 + 15) & ~15) >> 3;
+    if (kc1 * (2048 + (size_t)D * 16) > 200 * 1024 || kc2 * (2048 + (size_t)D * 16) > 200 * 1024) return false;
+    return aligned16(f1) && aligned16(f2) && aligned16(g) && aligned16(d1) && aligned16(d2);
+}
+
+int launch_corr_build_bwd_tc(int B, int D, int H, int W1, int W2, const void* f1, const void* f2, const void* g, void* df1,
+                             void* df2, cudaStream_t stream) {
+    const uint32_t cols = D <= 32 ? 32u : D <= 64 ? 64u : D <= 128 ? 128u : 256u;
+    const float div = sqrtf((float)D);
+    const size_t kc1 = (size_t)((W2 + 15) & ~15) >> 3, kc2 = (size_t)((W1 + 15) & ~15) >> 3;
+    const size_t smem1 = kc1 * (2048 + (size_t)D * 16), smem2 = kc2 * (2048 + (size_t)D * 16);
+    GPSG_REQUIRE((size_t)B * H <= 65535, "corr build backward: B*H too large");
+    GPSG_CUDA(cudaFuncSetAttribute(corr_build_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    GPSG_CUDA(cudaFuncSetAttribute(corr_build_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    corr_build_bwd_tc_kernel<false><<<dim3((W1 + kTcM - 1) / kTcM, B * H), kTcThreads, smem1, stream>>>(
+        D, H, W1, W2, (const __half*)f2, (const __half*)g, (__half*)df1, div, cols);
+    GPSG_LAUNCH_CHECK();
+    corr_build_bwd_tc_kernel<true><<<dim3(1, B * H), kTcThreads, smem2, stream>>>(D, H, W1, W2, (const __half*)f1,
+                                                                                (const __half*)g, (__half*)df2, div, cols);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
 }

@@ -186,6 +186,10 @@ int launch_corr_build(int dtype, int B, int D, int H, int W1, int W2, const void
 bool corr_build_tc_supported(int dtype, int D, int W1, int W2, const void* f1, const void* f2, void* const* v, int levels);
 int launch_corr_build_tc(int B, int D, int H, int W1, int W2, const void* f1, const void* f2, void* v0, void* v1, void* v2,
                          void* v3, int levels, cudaStream_t stream);
+bool corr_build_bwd_tc_supported(int dtype, int D, int W1, int W2, const void* f1, const void* f2, const void* g,
+                                 const void* d1, const void* d2);
+int launch_corr_build_bwd_tc(int B, int D, int H, int W1, int W2, const void* f1, const void* f2, const void* g, void* df1,
+                             void* df2, cudaStream_t stream);
 int launch_corr_build_bwd(int dtype, int B, int D, int H, int W1, int W2, const void* f1, const void* f2, const void* g,
                           void* df1, void* df2, cudaStream_t stream);
 int launch_corr_lookup_fwd(int dtype, int B, int H, int W1, const void* const* vols, const int* widths, int levels,

@@ -208,3 +208,40 @@ def test_tcgen05_build_falls_back_for_unsupported_shapes():
         got = CorrBlockFast1D(f1, f2, num_levels=2, radius=4).corr_pyramid[0].squeeze(3).float()
         ref = torch.einsum("bdhx,bdhy->bhxy", f1.double(), f2.double()) / D ** 0.5
         assert float((got.double() - ref).abs().max()) < 3e-3 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("shape", [(2, 192, 4, 128, 128), (1, 64, 2, 152, 48), (1, 32, 2, 264, 128), (1, 256, 1, 64, 64),
+                                   (1, 16, 1, 8, 16), (1, 48, 3, 72, 112)])
+def test_fp16_tcgen05_build_backward_matches_ffma_kernel_and_fp64(shape):
+    """gpsg_corr_build_backward in fp16: tcgen05 kernels (K-major and MN-major g operand) vs the FFMA kernels
+    (GPSG_CORR_BUILD=ffma) vs fp64 contractions; ragged M tiles and K padded to 16 (W1 = 152, 264, 72, 8)."""
+    import ctypes as C
+    from gps_gaussian_b200 import _lib
+    B, D, H, W1, W2 = shape
+    gen = torch.Generator("cuda").manual_seed(13)
+    f1 = torch.randn(B, D, H, W1, device="cuda", generator=gen).half()
+    f2 = torch.randn(B, D, H, W2, device="cuda", generator=gen).half()
+    g = torch.randn(B, H, W1, W2, device="cuda", generator=gen).half()
+    p = lambda t: C.c_void_p(t.data_ptr())
+
+    def run():
+        d1, d2 = torch.full_like(f1, float("nan")), torch.full_like(f2, float("nan"))
+        rc = _lib.lib.gpsg_corr_build_backward(0, C.c_void_p(torch.cuda.current_stream().cuda_stream), 1, B, D, H, W1, W2,
+                                               p(f1), p(f2), p(g), p(d1), p(d2))
+        _lib.check(rc, "gpsg_corr_build_backward")
+        torch.cuda.synchronize()
+        return d1, d2
+
+    tc = run()
+    os.environ["GPSG_CORR_BUILD"] = "ffma"
+    try:
+        ff = run()
+    finally:
+        os.environ.pop("GPSG_CORR_BUILD")
+    r1 = torch.einsum("bhxy,bdhy->bdhx", g.double(), f2.double()) / D ** 0.5
+    r2 = torch.einsum("bhxy,bdhx->bdhy", g.double(), f1.double()) / D ** 0.5
+    for a, b_, ref in ((tc[0], ff[0], r1), (tc[1], ff[1], r2)):
+        assert torch.isfinite(a).all()
+        scale = max(1.0, float(ref.abs().max()))
+        assert float((a.double() - ref).abs().max()) < 4e-3 * scale
+        assert float((a.float() - b_.float()).abs().max()) <= 2.0 ** -9 * scale       # same value up to one fp16 ulp
