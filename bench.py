@@ -232,6 +232,25 @@ def _corr_section(dev, hbm_peak_gbs):
     os.environ["GPSG_CORR_BUILD"] = "ffma"
     out["build_fwd_bwd_fp16_ffma_ms"] = timed(bwd, 20)
     os.environ.pop("GPSG_CORR_BUILD")
+    # CPU port beside it (oracle, scalar C, 1 thread) on a bounded sample: 8 of the 128 rows of the same problem
+    try:
+        from oracle.corr_oracle import CorrOracle
+        co = CorrOracle("f32")
+        hs = 8
+        n1, n2 = f32[0][:, :, :hs].cpu().numpy().copy(), f32[1][:, :, :hs].cpu().numpy().copy()
+        cs = coords[:, :, :hs].cpu().numpy().copy()
+        t0 = time.perf_counter()
+        pyr = co.pyramid(n1, n2, 4)
+        t_build = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        co.lookup(pyr, cs, 4)
+        t_look = time.perf_counter() - t0
+        out["cpu_port"] = {"sample": f"rows 0..{hs - 1} of {H} (1/{H // hs} of the work), oracle C port, 1 thread",
+                           "build_ms_sample": t_build * 1e3, "lookup_ms_sample": t_look * 1e3,
+                           "build_ms_full_extrapolated": t_build * 1e3 * H / hs,
+                           "lookup_ms_full_extrapolated": t_look * 1e3 * H / hs}
+    except Exception as exc:
+        out["cpu_port"] = {"error": repr(exc)}
     out["build_fp16_tcgen05_gbps"] = alg(2) / (out["build_fp16_tcgen05_ms"] * 1e-3) / 1e9
     out["build_fp16_tcgen05_hbm_frac"] = out["build_fp16_tcgen05_gbps"] / hbm_peak_gbs
     out["note"] = "wall of the Python call (allocation of the 4 level tensors + 1 launch), CUDA events, back-to-back"
@@ -397,6 +416,31 @@ def main():
     e2e_val = V * ksteps * world / (e2e_ms * 1e-3)
     # cross-check the last image of the step against the device-resident render of the same scene
     e2e_err = float((out_host[V - 1].to(dev) - calls[V - 1].color).abs().max())
+    # what bounds it: the host link.  Pinned H2D / D2H copy bandwidth of this box, alone and both directions at once,
+    # with the same per-view transfer sizes (28 MB in, 12.6 MB out).
+    link = {}
+    if rank == 0:
+        hbuf, dbuf = host[0][0][0], torch.empty_like(host[0][0][0], device=dev)
+        dimg = torch.empty((3, RES, RES), dtype=torch.float32, device=dev)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+        def both(n):
+            for _ in range(n):
+                with torch.cuda.stream(s_in):
+                    dbuf.copy_(hbuf, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    out_host[0].copy_(dimg, non_blocking=True)
+        for name, fn, nbytes in (("h2d_alone_gbps", lambda n: [dbuf.copy_(hbuf, non_blocking=True) for _ in range(n)], hbuf.numel() * 4),
+                                 ("d2h_alone_gbps", lambda n: [out_host[0].copy_(dimg, non_blocking=True) for _ in range(n)], dimg.numel() * 4),
+                                 ("h2d_while_d2h_gbps", both, hbuf.numel() * 4)):
+            fn(3)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn(20)
+            torch.cuda.synchronize()
+            link[name] = 20 * nbytes / (time.perf_counter() - t0) / 1e9
+        link["e2e_h2d_gbps"] = e2e_val / world * (h2d / V) / 1e9
+        link["e2e_frac_of_link"] = link["e2e_h2d_gbps"] / link["h2d_while_d2h_gbps"]
 
     # ---- reference-signature pts2render(data, bg_color): fused map ingest vs the reference's gather data flow ----
     from gps_gaussian_b200 import synth as _synth
@@ -587,7 +631,8 @@ def main():
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "gps_gaussian_b200.pipeline.HostRenderPipeline -> gaussian_renderer.render(data, idx, ...); pinned-host "
-                           "inputs, 3-stream H2D/compute/D2H overlap, host wall clock", "max_abs_diff_vs_device_path": e2e_err},
+                           "inputs, 3-stream H2D/compute/D2H overlap, host wall clock", "max_abs_diff_vs_device_path": e2e_err,
+                    "host_link": link},
             "gpu_launches": int(own), "cub_launches": int(cubl), "clocks": clocks}
     if train:
         line["train"] = train
