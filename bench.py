@@ -266,6 +266,7 @@ def main():
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the independent views of a step are issued on")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU-local NUMA node")
     ap.add_argument("--train", action="store_true", help="also time forward+backward (training replay)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -284,6 +285,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     from gps_gaussian_b200 import shard
+    numa = shard.bind_host_to_gpu(local_rank) if not args.no_numa_bind else {"bound": False, "why": "--no-numa-bind"}
     shard.init(backend="nccl", device=dev)
 
     from gps_gaussian_b200 import _lib
@@ -605,6 +607,7 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        shard.unbind_host()                                      # the CPU arm may use every host core
         vps, threads, dt = _cpu_oracle_views_per_sec(scenes[0], 8)
         cpu = {"value": vps, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"8 forward renders of one C2 view ({dt:.1f} s), CPU oracle port, OpenMP compositing",
@@ -632,7 +635,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "gps_gaussian_b200.pipeline.HostRenderPipeline -> gaussian_renderer.render(data, idx, ...); pinned-host "
                            "inputs, 3-stream H2D/compute/D2H overlap, host wall clock", "max_abs_diff_vs_device_path": e2e_err,
-                    "host_link": link},
+                    "host_link": link, "host_numa_binding": numa},
             "gpu_launches": int(own), "cub_launches": int(cubl), "clocks": clocks}
     if train:
         line["train"] = train

@@ -42,6 +42,47 @@ def init(backend=None, device=None):
     return rank, ws
 
 
+def bind_host_to_gpu(local_rank):
+    """Pin this process to the CPUs that are NUMA-local to GPU `local_rank` (NVML's ideal affinity) so that the pinned
+    host buffers it allocates afterwards, and the copies it drives, stay on the socket the GPU hangs off: with one process
+    per GPU, host-link transfers of different ranks then do not cross the inter-socket fabric.  Best effort: returns a
+    small dict describing what happened (never raises)."""
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        try:                                                    # CUDA ordinal -> NVML handle through the PCI address
+            import torch                                        # (CUDA_VISIBLE_DEVICES can renumber the CUDA side)
+            pr = torch.cuda.get_device_properties(int(local_rank))
+            bus = "%08X:%02X:%02X.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            info["pci"] = bus
+        except Exception:
+            h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(local_rank))
+        before = len(os.sched_getaffinity(0))
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update({"bound": True, "cpus": len(cpus), "cpus_before": before})
+    except Exception as exc:                                    # containers may forbid it; the run is still valid
+        info = {"bound": False, "why": repr(exc)[:120]}
+    return info
+
+
+def unbind_host():
+    """Undo bind_host_to_gpu (e.g. before timing a CPU baseline on all host cores)."""
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count()))
+    except Exception:
+        pass
+
+
 def shard_units(n_units, rank, world_size):
     """Contiguous block partition of unit ids 0..n_units-1; sizes differ by at most one; every unit exactly once."""
     base, rem = divmod(n_units, world_size)
