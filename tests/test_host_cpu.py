@@ -43,6 +43,18 @@ def test_argument_validation_without_gpu(built_lib):
     assert _lib.lib.gpsg_corr_sampler_forward(0, None, 7, 1, 1, 1, 1, None, 0, 0, 0, None, 0, 4, None) == -1
     assert _lib.lib.gpsg_corr_sampler_forward(0, None, 0, 0, 4, 4, 4, None, 0, 0, 0, None, 0, 4, None) == 0   # empty batch: no-op
     assert _lib.lib.gpsg_rasterize_backward_workspace_bytes(1000) >= 16000
+    # the newer rows: shape / pointer validation happens before any CUDA call
+    assert _lib.lib.gpsg_l1_ssim_forward(0, None, 0, 8, 8, None, None, 0.8, 0.2, None, None, None) == -1
+    assert b"empty image" in _lib.lib.gpsg_last_error()
+    assert _lib.lib.gpsg_l1_ssim_workspace_bytes(3, 1024, 1024) >= 2 * 8 * 3 * 32 * 32
+    assert _lib.lib.gpsg_corr_build_backward(0, None, 5, 1, 16, 1, 8, 16, None, None, None, None, None) == -1
+    assert _lib.lib.gpsg_corr_build_backward(0, None, 1, 0, 16, 1, 8, 16, None, None, None, None, None) == 0   # empty batch
+    assert _lib.lib.gpsg_unproject_forward(0, None, 0, 16, None, None, 0, None, None, 3, None, None, None, None, None) == 0
+    s.image_height = 16
+    pp = (C.c_void_p * 2)()
+    rc = _lib.lib.gpsg_rasterize_forward_maps_planned(C.byref(s), 0, None, 0, pp, pp, pp, pp, pp, pp, None, None, None, None,
+                                                      1, None, None)
+    assert rc == -1 and b"pixels per view" in _lib.lib.gpsg_last_error()
 
 
 def test_dropin_api_surface(built_lib):
@@ -78,6 +90,14 @@ def test_mirrored_interface_names():
     sig = inspect.signature(corr.CorrBlockFast1D.__init__).parameters
     assert list(sig) == ["self", "fmap1", "fmap2", "num_levels", "radius"] and sig["radius"].default == 4
     assert hasattr(corr, "CorrSampler")
+    from gps_gaussian_b200 import loss, novel_calib, shard, unproject
+    assert list(inspect.signature(novel_calib.get_novel_calib).parameters) == ["data", "opt", "ratio", "intr_key", "extr_key"]  # lib/utils.py:8
+    assert list(inspect.signature(loss.ssim).parameters) == ["img1", "img2", "window_size", "size_average"]   # lib/loss.py:52
+    assert list(inspect.signature(loss.l1_loss).parameters) == ["network_output", "gt"]                          # lib/loss.py:35
+    assert hasattr(unproject, "flow2xyz")
+    info = shard.bind_host_to_gpu(0)            # no NVML here: must degrade to a no-op description, never raise
+    assert isinstance(info, dict) and "bound" in info
+    shard.unbind_host()
 
 
 def test_synth_matches_reference_conventions():
