@@ -166,7 +166,8 @@ def end_alloc():
 
 
 def profile_enable(on=True):
-    check(lib.gpsg_profile_enable(1 if on else 0), "gpsg_profile_enable")
+    """True / 1: CUDA events around every stage + launch counts; 2: launch counts only; False: off."""
+    check(lib.gpsg_profile_enable(2 if on == 2 else (1 if on else 0)), "gpsg_profile_enable")
 
 
 def profile_read():

@@ -152,7 +152,7 @@ static uint32_t* pinned_slot() {
 namespace gpsg {
 struct ProfSlot { cudaEvent_t a, b; Stage stage; bool used; };
 struct Profiler {
-    bool on = false;
+    int on = 0;                      // 0 off, 1 events + launch counts, 2 launch counts only
     std::vector<ProfSlot> slots;
     size_t next = 0;
     int launches[ST_COUNT] = {0};
@@ -163,6 +163,7 @@ static const char* kStageNames[ST_COUNT] = {"preprocess", "scan", "duplicate", "
                                             "render_backward", "preprocess_backward", "corr_forward", "corr_backward", "corr_build"};
 StageTimer::StageTimer(Stage s, cudaStream_t st, int launches) : stage(s), stream(st), slot(nullptr) {
     if (!g_prof.on) return;
+    if (g_prof.on == 2) { g_prof.launches[s] += launches; return; }
     if (g_prof.next == g_prof.slots.size()) {
         ProfSlot ps; ps.used = false;
         if (cudaEventCreate(&ps.a) != cudaSuccess || cudaEventCreate(&ps.b) != cudaSuccess) return;
@@ -647,7 +648,7 @@ int gpsg_l1_ssim_backward(int device, void* stream_, int planes, int H, int W, c
 }
 
 int gpsg_profile_enable(int on) {
-    g_prof.on = on != 0;
+    g_prof.on = on == 2 ? 2 : (on != 0);
     return GPSG_OK;
 }
 const char* gpsg_profile_stage_name(int stage) { return (stage >= 0 && stage < ST_COUNT) ? kStageNames[stage] : ""; }
