@@ -4,6 +4,9 @@
 #include "gpsg_internal.cuh"
 #include "slab_ring.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace gpsg {
 
 constexpr int kBwdChunk = 64;   // Gaussians per ring stage
@@ -188,12 +191,211 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32) render_backward_kernel(c
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// A.6, second formulation: pixel-major replay + GAUSSIAN-major reduction.
+// The butterfly above spends ~2/3 of its instructions reducing 9 per-pixel products per survivor across the warp.  Here the
+// sequential part (per pixel, back to front: alpha, T, the running colour) only produces the two scalars every gradient
+// term is linear in,  s = G * opacity * dL/dalpha  and  w = alpha * T,  and parks them in shared memory, one row of 32 pixels
+// per surviving Gaussian.  Once kQ = 16 rows are parked the roles flip: lane (j, h) owns Gaussian j and pixel rows
+// [2h, 2h+1] of the warp's 8x4 block, walks its 16 pixels accumulating the 9 sums
+//   sum s*dx, s*dy, s*dx^2, s*dx*dy, s*dy^2, s   and   sum w*g_r, w*g_g, w*g_b
+// in registers -- no shuffles -- then the two halves are added with one shuffle per value and each lane issues the global
+// REDs of its Gaussian.  Rows are padded to 33 floats: conflict-free both when a pixel-lane writes column `lane` of row
+// `slot` and when Gaussian-lanes read `row j, column p`.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kQ = 16;
+constexpr int kBwdStages2 = 6;
+struct __align__(16) BwdWarpBuf {
+    float4 gpix[32];        // (g_r, g_g, g_b, 0) of the warp's 32 pixels
+    float4 meta[kQ];        // (mean x, mean y, id bits, 0) of the parked Gaussians
+    float S[kQ][33];
+    float Wt[kQ][33];
+};
+
+__global__ void __launch_bounds__((kBwdWarps + 1) * 32) render_backward_gm_kernel(const __grid_constant__ Camera cam,
+                                                                                const float4* __restrict__ slabA,
+                                                                                const float4* __restrict__ slabB,
+                                                                                const float4* __restrict__ slabC,
+                                                                                const uint2* __restrict__ ranges, const uint32_t* __restrict__ status,
+                                                                                const float* __restrict__ final_T,
+                                                                                const uint32_t* __restrict__ n_contrib,
+                                                                                const float* __restrict__ dL_dpix,
+                                                                                float* __restrict__ dL_dmeans2D,
+                                                                                float4* __restrict__ dL_dconic_op,
+                                                                                float* __restrict__ dL_dcolors) {
+    __shared__ SlabRing<kBwdChunk, kBwdStages2> ring;
+    __shared__ BwdWarpBuf wbuf[kBwdWarps];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_y = blockIdx.y >> 1, half = blockIdx.y & 1;
+    const int tile = tile_y * cam.grid_x + blockIdx.x;
+    const uint2 range = status[2] ? make_uint2(0u, 0u) : ranges[tile];   // planned-mode overflow: render nothing
+    const int total = (int)(range.y - range.x);
+
+    const int bx0 = blockIdx.x * GPSG_TILE_X + ((warp & 1) << 3);
+    const int by0 = tile_y * GPSG_TILE_Y + (half << 3) + ((warp >> 1) << 2);
+    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+    const bool inside = warp < kBwdWarps && px < cam.W && py < cam.H;
+    const float pixfx = (float)px, pixfy = (float)py;
+    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
+    const size_t HW = (size_t)cam.W * cam.H;
+    const size_t pid = (size_t)py * cam.W + px;
+    const float T_final = inside ? final_T[pid] : 0.0f;
+    const int last_contributor = inside ? (int)n_contrib[pid] : 0;
+    const int wmax = __reduce_max_sync(0xffffffffu, last_contributor);
+
+    if (tid == 0) ring_init(ring, kBwdWarps);
+    __syncthreads();
+    if (lane == 0 && wmax > 0) atomicMax(&ring.hi, wmax);
+    __syncthreads();
+    const int hi = min(total, *(volatile int*)&ring.hi);
+    const int nbatch = (hi + kBwdChunk - 1) / kBwdChunk;
+
+    if (warp == kBwdWarps) {  // ---------------- producer warp ----------------
+        if (lane == 0)
+            ring_produce(ring, nbatch, kBwdWarps, slabA, slabB, slabC,
+                         [&](int b) { const int end = hi - b * kBwdChunk; return (size_t)range.x + (size_t)(end - min(kBwdChunk, end)); },
+                         [&](int b) { return min(kBwdChunk, hi - b * kBwdChunk); });
+        return;
+    }
+
+    BwdWarpBuf& wb = wbuf[warp];
+    float T = T_final;
+    float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f, lastc0 = 0.f, lastc1 = 0.f, lastc2 = 0.f, last_alpha = 0.f;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    if (inside) { g0 = dL_dpix[pid]; g1 = dL_dpix[HW + pid]; g2 = dL_dpix[2 * HW + pid]; }
+    wb.gpix[lane] = make_float4(g0, g1, g2, 0.f);
+    __syncwarp();
+    const float bg_dot = (cam.bg[0] * g0 + cam.bg[1] * g1) + cam.bg[2] * g2;
+
+    // Gaussian-major role of this lane: Gaussian slot qj, pixel rows 2*qh and 2*qh+1 of the block
+    const int qj = lane & (kQ - 1), qh = lane >> 4;
+    const float fx0 = (float)bx0, fy0 = (float)(by0 + 2 * qh);
+    int slot = 0;
+
+    auto flush = [&](int cnt) {
+        __syncwarp();
+        const float4 me = wb.meta[qj];
+        const bool on = qj < cnt;
+        const float dxb = me.x - fx0, dy0 = me.y - fy0, dy1 = dy0 - 1.0f;
+        float m0 = 0.f, m1 = 0.f, k0 = 0.f, k1 = 0.f, k2 = 0.f, k3 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < 16; ++pp) {
+            const int p = qh * 16 + pp;
+            const float sv = wb.S[qj][p];
+            const float wv = wb.Wt[qj][p];
+            const float4 gp = wb.gpix[p];
+            const float dx = dxb - (float)(pp & 7);
+            const float dy = (pp & 8) ? dy1 : dy0;
+            const float sx = sv * dx, sy = sv * dy;
+            m0 += sx;
+            m1 += sy;
+            k0 = fmaf(sx, dx, k0);
+            k1 = fmaf(sx, dy, k1);
+            k2 = fmaf(sy, dy, k2);
+            k3 += sv;
+            c0 = fmaf(wv, gp.x, c0);
+            c1 = fmaf(wv, gp.y, c1);
+            c2 = fmaf(wv, gp.z, c2);
+        }
+        m0 += __shfl_xor_sync(0xffffffffu, m0, 16);
+        m1 += __shfl_xor_sync(0xffffffffu, m1, 16);
+        k0 += __shfl_xor_sync(0xffffffffu, k0, 16);
+        k1 += __shfl_xor_sync(0xffffffffu, k1, 16);
+        k2 += __shfl_xor_sync(0xffffffffu, k2, 16);
+        k3 += __shfl_xor_sync(0xffffffffu, k3, 16);
+        c0 += __shfl_xor_sync(0xffffffffu, c0, 16);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, 16);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, 16);
+        if (on) {
+            const uint32_t id = __float_as_uint(me.z);
+            float* cop = reinterpret_cast<float*>(dL_dconic_op + id);
+            if (qh == 0) {      // lower half of the warp: mean + three conic moments
+                if (m0 != 0.f) atomicAdd(dL_dmeans2D + 3 * (size_t)id, m0);
+                if (m1 != 0.f) atomicAdd(dL_dmeans2D + 3 * (size_t)id + 1, m1);
+                if (k0 != 0.f) atomicAdd(cop, k0);
+                if (k1 != 0.f) atomicAdd(cop + 1, k1);
+                if (k2 != 0.f) atomicAdd(cop + 2, k2);
+            } else {            // upper half: opacity moment + colour
+                if (k3 != 0.f) atomicAdd(cop + 3, k3);
+                if (c0 != 0.f) atomicAdd(dL_dcolors + 3 * (size_t)id, c0);
+                if (c1 != 0.f) atomicAdd(dL_dcolors + 3 * (size_t)id + 1, c1);
+                if (c2 != 0.f) atomicAdd(dL_dcolors + 3 * (size_t)id + 2, c2);
+            }
+        }
+        __syncwarp();
+    };
+
+    for (int b = 0; b < nbatch; ++b) {
+        ring_wait_full(ring, b, kBwdWarps + 1 /* never "all done" in the backward */);
+        const int s = b % kBwdStages2;
+        const int end = hi - b * kBwdChunk;
+        const int n = min(kBwdChunk, end);
+        const int start = end - n;
+        if (start < wmax) {
+            const float4* __restrict__ SA = ring.A[s];
+            const float4* __restrict__ SB = ring.B[s];
+            const float4* __restrict__ SC = ring.C[s];
+            for (int base = ((n - 1) >> 5) << 5; base >= 0; base -= 32) {
+                if (start + base >= wmax) continue;
+                const int my = base + lane;
+                bool hit = false;
+                if (my < n && start + my < wmax) {
+                    const float4 a = SA[my];
+                    hit = (a.x >= wx0 - a.z) && (a.x <= wx1 + a.z) && (a.y >= wy0 - a.w) && (a.y <= wy1 + a.w);
+                }
+                unsigned m = __ballot_sync(0xffffffffu, hit);
+                while (m) {
+                    const int bit = 31 - __clz(m);             // back to front: deepest surviving entry first
+                    m &= ~(1u << bit);
+                    const int j = base + bit;
+                    const float2 xy = *reinterpret_cast<const float2*>(&SA[j]);
+                    const float4 q = SB[j];
+                    const float4 c = SC[j];
+                    const float dx = xy.x - pixfx, dy = xy.y - pixfy;
+                    const float p = fmaf(q.z * dy, dy, fmaf(q.x, dx, q.y * dy) * dx);   // log2e * power
+                    const float G = ex2_approx(p);
+                    const float alpha = fminf(0.99f, q.w * G);
+                    const bool active = (start + j) < last_contributor && !(p > 0.0f) && !(alpha < 1.0f / 255.0f);
+                    if (!__any_sync(0xffffffffu, active)) continue;
+                    float inv1ma;                                 // 1 - alpha >= 0.01: MUFU.RCP (1 ulp) without the slow path
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1ma) : "f"(1.0f - alpha));
+                    const float Tn = T * inv1ma;
+                    const float a0 = fmaf(last_alpha, lastc0 - accum0, accum0);
+                    const float a1 = fmaf(last_alpha, lastc1 - accum1, accum1);
+                    const float a2 = fmaf(last_alpha, lastc2 - accum2, accum2);
+                    float dL_dalpha = (c.x - a0) * g0;
+                    dL_dalpha = fmaf(c.y - a1, g1, dL_dalpha);
+                    dL_dalpha = fmaf(c.z - a2, g2, dL_dalpha);
+                    dL_dalpha = fmaf(dL_dalpha, Tn, (-T_final * inv1ma) * bg_dot);
+                    wb.S[slot][lane] = active ? G * (q.w * dL_dalpha) : 0.0f;
+                    wb.Wt[slot][lane] = active ? alpha * Tn : 0.0f;
+                    if (lane == 0) wb.meta[slot] = make_float4(xy.x, xy.y, c.w, 0.f);
+                    T = active ? Tn : T;
+                    accum0 = active ? a0 : accum0; accum1 = active ? a1 : accum1; accum2 = active ? a2 : accum2;
+                    lastc0 = active ? c.x : lastc0; lastc1 = active ? c.y : lastc1; lastc2 = active ? c.z : lastc2;
+                    last_alpha = active ? alpha : last_alpha;
+                    if (++slot == kQ) { flush(kQ); slot = 0; }
+                }
+            }
+        }
+        ring_release(ring, b, lane);
+    }
+    if (slot > 0) flush(slot);
+}
+
 int launch_render_backward(const Camera& cam, BinningState b, ImageState im, const float* dL_dpix, float* dL_dmeans2D,
                            float4* dL_dconic_op, float* dL_dcolors, cudaStream_t stream) {
     dim3 grid(cam.grid_x, cam.grid_y * 2);
-    render_backward_kernel<<<grid, (kBwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges, im.totals,
-                                                                     im.final_T, im.n_contrib, dL_dpix, dL_dmeans2D,
-                                                                     dL_dconic_op, dL_dcolors);
+    const char* e = getenv("GPSG_BWD");                       // "butterfly" selects the first formulation
+    if (e && strcmp(e, "butterfly") == 0)
+        render_backward_kernel<<<grid, (kBwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges, im.totals,
+                                                                         im.final_T, im.n_contrib, dL_dpix, dL_dmeans2D,
+                                                                         dL_dconic_op, dL_dcolors);
+    else
+        render_backward_gm_kernel<<<grid, (kBwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges,
+                                                                            im.totals, im.final_T, im.n_contrib, dL_dpix,
+                                                                            dL_dmeans2D, dL_dconic_op, dL_dcolors);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
 }
