@@ -204,7 +204,6 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32) render_backward_kernel(c
 // `slot` and when Gaussian-lanes read `row j, column p`.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kQ = 16;
-constexpr int kBwdStages2 = 6;
 struct __align__(16) BwdWarpBuf {
     float4 gpix[32];        // (g_r, g_g, g_b, 0) of the warp's 32 pixels
     float4 meta[kQ];        // (mean x, mean y, id bits, 0) of the parked Gaussians
@@ -212,7 +211,10 @@ struct __align__(16) BwdWarpBuf {
     float Wt[kQ][33];
 };
 
-__global__ void __launch_bounds__((kBwdWarps + 1) * 32) render_backward_gm_kernel(const __grid_constant__ Camera cam,
+// STAGES x 64-entry ring, MIN_BLOCKS CTAs / SM.  Measured on C2: <8,5> 303 us, <6,5> 327, <5,6> 333, <4,6> 353 -- the
+// producer lane needs the deeper ring more than the SM needs a sixth CTA (44.8 KB of static shared memory / CTA: 5 fit).
+template <int STAGES, int MIN_BLOCKS>
+__global__ void __launch_bounds__((kBwdWarps + 1) * 32, MIN_BLOCKS) render_backward_gm_kernel(const __grid_constant__ Camera cam,
                                                                                 const float4* __restrict__ slabA,
                                                                                 const float4* __restrict__ slabB,
                                                                                 const float4* __restrict__ slabC,
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32) render_backward_gm_kerne
                                                                                 float* __restrict__ dL_dmeans2D,
                                                                                 float4* __restrict__ dL_dconic_op,
                                                                                 float* __restrict__ dL_dcolors) {
-    __shared__ SlabRing<kBwdChunk, kBwdStages2> ring;
+    __shared__ SlabRing<kBwdChunk, STAGES> ring;
     __shared__ BwdWarpBuf wbuf[kBwdWarps];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32) render_backward_gm_kerne
 
     for (int b = 0; b < nbatch; ++b) {
         ring_wait_full(ring, b, kBwdWarps + 1 /* never "all done" in the backward */);
-        const int s = b % kBwdStages2;
+        const int s = b % STAGES;
         const int end = hi - b * kBwdChunk;
         const int n = min(kBwdChunk, end);
         const int start = end - n;
@@ -393,9 +395,9 @@ int launch_render_backward(const Camera& cam, BinningState b, ImageState im, con
                                                                          im.final_T, im.n_contrib, dL_dpix, dL_dmeans2D,
                                                                          dL_dconic_op, dL_dcolors);
     else
-        render_backward_gm_kernel<<<grid, (kBwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges,
-                                                                            im.totals, im.final_T, im.n_contrib, dL_dpix,
-                                                                            dL_dmeans2D, dL_dconic_op, dL_dcolors);
+        render_backward_gm_kernel<8, 5><<<grid, (kBwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges,
+                                                                                  im.totals, im.final_T, im.n_contrib, dL_dpix,
+                                                                                  dL_dmeans2D, dL_dconic_op, dL_dcolors);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
 }
