@@ -113,3 +113,41 @@ def test_synth_matches_reference_conventions():
     hom = np.concatenate([sc["means3D"][:100], np.ones((100, 1), np.float32)], 1)
     assert np.allclose((hom @ sc["proj"])[:, 3], (hom @ v)[:, 2], atol=1e-5)   # clip-space w == view-space depth (P[3,2] = 1)
     assert ((hom @ v)[:, 2] > 1.0).all()                            # the body is in front of the novel camera
+
+
+def test_render_mirror_passes_what_the_rasterizer_module_would(built_lib, monkeypatch):
+    """`render()` enters the autograd function directly; the arguments must equal what
+    GaussianRasterizer(raster_settings)(means3D=..., means2D=..., shs=None, colors_precomp=..., ...) hands over
+    (reference gaussian_renderer/__init__.py:36-62)."""
+    import math
+    from gps_gaussian_b200 import gaussian_renderer as gr
+    import diff_gaussian_rasterization as dgr
+    seen = []
+    monkeypatch.setattr(dgr, "rasterize_gaussians", lambda *a: (seen.append(a), (torch.zeros(3, 4, 4), None))[1])
+    P = 5
+    xyz, rgb = torch.randn(P, 3, requires_grad=True), torch.rand(P, 3)
+    rot, sc, op = torch.randn(P, 4), torch.rand(P, 3), torch.rand(P, 1)
+    nv = {"FovX": torch.tensor([0.9, 1.1], dtype=torch.float64), "FovY": torch.tensor([0.8, 1.0], dtype=torch.float64),
+          "height": torch.tensor([32, 48]), "width": torch.tensor([40, 56]),
+          "world_view_transform": torch.randn(2, 4, 4), "full_proj_transform": torch.randn(2, 4, 4),
+          "camera_center": torch.randn(2, 3)}
+    out = gr.render({"novel_view": nv}, 1, xyz, rgb, rot, sc, op, [0.1, 0.2, 0.3])
+    assert out.shape == (3, 4, 4)
+    direct = seen.pop()
+    rs = dgr.GaussianRasterizationSettings(image_height=48, image_width=56, tanfovx=math.tan(0.55), tanfovy=math.tan(0.5),
+                                           bg=torch.tensor([0.1, 0.2, 0.3]), scale_modifier=1.0,
+                                           viewmatrix=nv["world_view_transform"][1], projmatrix=nv["full_proj_transform"][1],
+                                           sh_degree=3, campos=nv["camera_center"][1], prefiltered=False, debug=False)
+    sink = torch.zeros_like(xyz)
+    dgr.GaussianRasterizer(raster_settings=rs)(means3D=xyz, means2D=sink, shs=None, colors_precomp=rgb, opacities=op,
+                                               scales=sc, rotations=rot, cov3D_precomp=None)
+    via_module = seen.pop()
+    assert len(direct) == len(via_module) == 9
+    for k, (a, b) in enumerate(zip(direct[:8], via_module[:8])):
+        assert a.shape == b.shape and a.dtype == b.dtype and torch.equal(a.detach(), b.detach()), k
+    assert direct[1].requires_grad and direct[1].grad_fn is not None          # the means2D gradient sink is live
+    sa, sb = dgr._pack_settings(direct[8]), dgr._pack_settings(via_module[8])
+    assert bytes(sa) == bytes(sb)                                              # identical by-value camera struct
+    with torch.no_grad():
+        gr.render({"novel_view": nv}, 0, xyz, rgb, rot, sc, op, [0, 0, 0])
+    assert not seen.pop()[1].requires_grad
