@@ -84,3 +84,43 @@ def test_synthetic_dataset_is_read_by_the_reference_loader(tmp_path):
     t = StereoHumanDataset(opt, phase="test").get_test_item(0, source_id=[0, 1])
     assert tuple(t["lmain"]["intr_ori"].shape) == (3, 3) and tuple(t["rmain"]["extr_ori"].shape) == (3, 4)
     assert int(t["novel_view"]["height"]) == 2 * res
+
+
+@needs_ref
+def test_import_hook_rebinds_the_reference_entry_points(tmp_path):
+    """GPSG_PATCH=1 + dropin/ on PYTHONPATH: `sitecustomize` installs the post-import hook, the reference's own
+    `from core.corr import CorrBlockFast1D` / `from lib.GaussianRender import pts2render` resolve to the fused paths;
+    without the variable nothing is touched."""
+    import subprocess
+    code = ("import core.raft_stereo_human as r, core.corr as c\n"
+            "from lib.GaussianRender import pts2render\n"
+            "print(r.CorrBlockFast1D.__module__, c.CorrSampler.__module__, pts2render.__module__)\n")
+    out = {}
+    for flag in ("0", "1"):
+        env = dict(os.environ, PYTHONPATH=os.pathsep.join([DROPIN, REF]), GPSG_PATCH=flag)
+        p = subprocess.run([sys.executable, "-c", code], env=env, cwd=str(tmp_path), capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr[-2000:]
+        out[flag] = p.stdout.split()
+    assert out["0"] == ["core.corr", "core.corr", "lib.GaussianRender"]
+    assert out["1"] == ["gps_gaussian_b200.corr", "gps_gaussian_b200.corr", "gps_gaussian_b200.GaussianRender"]
+
+
+@needs_ref
+def test_c3_harness_builds_the_reference_model_and_batch_on_cpu(tmp_path):
+    """Plumbing of gps_gaussian_b200.harness without a GPU: staging, config, the reference's loader + model (the
+    pure-PyTorch 'reg' correlation path), one forward.  The GPU half is tests/test_c3_gpu.py."""
+    from gps_gaussian_b200 import harness, synth_dataset
+    assert harness.stage_reference() is not None
+    for name in ("train_stage2.py", "core/corr.py", "lib/GaussianRender.py", "gaussian_renderer/__init__.py"):
+        with open(os.path.join(REF, name), "rb") as a, open(os.path.join(harness.REF_STAGED, name), "rb") as b:
+            assert a.read() == b.read()                                   # staged byte for byte
+    root = str(tmp_path / "data")
+    synth_dataset.write_dataset(root, n_train=2, n_val=1, res=128, hr=True)
+    cfg = harness.load_cfg(root, src_res=128, num_steps=3, batch_size=2, corr_implementation="reg")
+    assert cfg.stage1_ckpt is None and cfg.num_steps == 3 and cfg.dataset.data_root == root
+    st = harness.C3State(cfg, device="cpu")
+    data = st.batch(0)
+    assert tuple(data["lmain"]["img"].shape) == (2, 3, 128, 128) and tuple(data["novel_view"]["img"].shape) == (2, 3, 256, 256)
+    data, flow_loss, metrics = st.model(data, is_train=True)
+    assert tuple(data["lmain"]["xyz"].shape) == (2, 128 * 128, 3) and data["rmain"]["pts_valid"].dtype == torch.bool
+    assert bool(torch.isfinite(flow_loss)) and "train_epe" in metrics
