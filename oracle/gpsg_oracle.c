@@ -279,6 +279,68 @@ void SUFFIX(oracle_render)(int W, int H, const uint32_t* ranges, const uint32_t*
     }
 }
 
+/* ------------------------------------------------------------------ threshold margins (parity accounting) */
+/* A.4 has three hard decisions per evaluated (pixel, Gaussian) pair: `power > 0`, `alpha < 1/255`, `test_T < 1e-4`.
+ * Two correct implementations whose arithmetic differs by rounding (FMA, ex2.approx, op order) can take a decision
+ * differently ONLY where the tested quantity sits within rounding distance of its threshold; everywhere else their
+ * images agree to rounding.  This pass replays A.4 and records, per pixel, how close any decision the pixel actually
+ * took came to flipping:
+ *    m_alpha = min |alpha*255 - 1|        (relative distance of alpha to 1/255; pairs with power <= 0)
+ *    m_T     = min |test_T/1e-4 - 1|      (relative distance of the transmittance test)
+ *    m_power = min |power|                (absolute; power > 0 only happens through rounding of a near-singular conic)
+ * tests/ turn "up to x% of pixels may exceed 1e-4" into: every pixel outside the tolerance has a margin below eps.
+ * `taint` (may be NULL): per Gaussian, set to 1 if it is evaluated (alpha >= (1-eps_alpha)/255, power <= eps_power)
+ * by a pixel whose margins are below the eps triple -- its gradient can legitimately differ by a flipped decision. */
+void SUFFIX(oracle_render_margins)(int W, int H, const uint32_t* ranges, const uint32_t* point_list, const real* means2D,
+                                   const real* conic_opacity, double eps_alpha, double eps_T, double eps_power,
+                                   /* out */ double* m_alpha, double* m_T, double* m_power, uint8_t* taint, int nthreads) {
+    const int gx = (W + BLOCK_X - 1) / BLOCK_X;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads > 0 ? nthreads : 1)
+#endif
+    for (int py = 0; py < H; ++py) {
+        for (int px = 0; px < W; ++px) {
+            int tile = (py / BLOCK_Y) * gx + (px / BLOCK_X);
+            uint32_t s = ranges[2 * tile], e = ranges[2 * tile + 1];
+            real pixfx = (real)px, pixfy = (real)py;
+            real T = RC(1.0);
+            double ma = 1e30, mt = 1e30, mp = 1e30;
+            for (uint32_t k = s; k < e; ++k) {
+                uint32_t id = point_list[k];
+                real dx = means2D[2 * id] - pixfx, dy = means2D[2 * id + 1] - pixfy;
+                const real* co = conic_opacity + 4 * id;
+                real power = RC(-0.5) * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+                double ap = fabs((double)power);
+                if (ap < mp) mp = ap;
+                if (power > (real)0) continue;
+                real alpha = rmin(RC(0.99), co[3] * R_EXP(power));
+                double da = fabs((double)alpha * 255.0 - 1.0);
+                if (da < ma) ma = da;
+                if (alpha < RC(1.0) / RC(255.0)) continue;
+                real test_T = T * (RC(1.0) - alpha);
+                double dt = fabs((double)test_T / 1e-4 - 1.0);
+                if (dt < mt) mt = dt;
+                if (test_T < RC(0.0001)) break;
+                T = test_T;
+            }
+            int64_t pid = (int64_t)py * W + px;
+            m_alpha[pid] = ma; m_T[pid] = mt; m_power[pid] = mp;
+            if (taint && (ma < eps_alpha || mt < eps_T || mp < eps_power)) {
+                for (uint32_t k = s; k < e; ++k) {
+                    uint32_t id = point_list[k];
+                    real dx = means2D[2 * id] - pixfx, dy = means2D[2 * id + 1] - pixfy;
+                    const real* co = conic_opacity + 4 * id;
+                    real power = RC(-0.5) * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+                    if ((double)power > eps_power) continue;
+                    real alpha = rmin(RC(0.99), co[3] * R_EXP(power));
+                    if ((double)alpha * 255.0 < 1.0 - eps_alpha) continue;
+                    taint[id] = 1; /* benign race: every writer stores 1 */
+                }
+            }
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ A.6 */
 /* dL_dmean2D: [P,2] (NDC-scaled, see A.6), dL_dconic: [P,3] = (x, y(half-convention), w), all zero-initialised here */
 void SUFFIX(oracle_render_backward)(int P, int W, int H, const uint32_t* ranges, const uint32_t* point_list,

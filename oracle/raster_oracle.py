@@ -124,6 +124,36 @@ class RasterOracle:
                                       _p(st["n_contrib"]), C.c_int(nthreads))
         return st
 
+    def render_state(self, st, nthreads=1):
+        """A.4 compositing in THIS oracle's precision on the per-Gaussian state (means2D, conic_opacity, colours, tile
+        lists) of a forward done in any precision -- isolates the compositing arithmetic from the projection's."""
+        W, H = st["W"], st["H"]
+        r = self.np
+        i = st["inputs"]
+        m2 = self._a(st["means2D"]); co = self._a(st["conic_opacity"]); col = self._a(i["colors"]); bg = self._a(i["bg"])
+        out = dict(color=np.zeros((3, H, W), r), final_T=np.zeros((H, W), r), n_contrib=np.zeros((H, W), np.uint32))
+        self._fn("oracle_render")(C.c_int(W), C.c_int(H), _p(st["ranges"]), _p(st["_vals_full"]), _p(m2), _p(col), _p(co),
+                                  _p(bg), _p(out["color"]), _p(out["final_T"]), _p(out["n_contrib"]), C.c_int(nthreads))
+        return out
+
+    # rounding-distance thresholds of the three hard decisions of A.4 (see oracle_render_margins in gpsg_oracle.c):
+    # relative on alpha vs 1/255 and test_T vs 1e-4, absolute on power vs 0.
+    EPS = dict(alpha=2e-5, T=2e-3, power=1e-5)
+
+    def margins(self, st, eps=None, nthreads=1):
+        """Per-pixel distance of the closest hard decision to its threshold, the `near` mask (a decision within eps:
+        the pixel may legitimately differ between two correct implementations) and the per-Gaussian `taint` flag
+        (evaluated by a `near` pixel: its gradient may legitimately differ)."""
+        eps = dict(self.EPS, **(eps or {}))
+        W, H, P = st["W"], st["H"], st["P"]
+        ma = np.zeros((H, W), np.float64); mt = np.zeros((H, W), np.float64); mp = np.zeros((H, W), np.float64)
+        taint = np.zeros(max(P, 1), np.uint8)
+        self._fn("oracle_render_margins")(C.c_int(W), C.c_int(H), _p(st["ranges"]), _p(st["_vals_full"]), _p(st["means2D"]),
+                                          _p(st["conic_opacity"]), C.c_double(eps["alpha"]), C.c_double(eps["T"]),
+                                          C.c_double(eps["power"]), _p(ma), _p(mt), _p(mp), _p(taint), C.c_int(nthreads))
+        near = (ma < eps["alpha"]) | (mt < eps["T"]) | (mp < eps["power"])
+        return dict(alpha=ma, T=mt, power=mp, near=near, taint=taint[:P].astype(bool), eps=eps)
+
     def backward(self, st, dL_dpix):
         P, W, H = st["P"], st["W"], st["H"]
         r = self.np

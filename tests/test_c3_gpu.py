@@ -78,15 +78,20 @@ def test_c3_step_against_dropins_finite_and_matches_oracle(dataset):
     # (a)
     assert math.isfinite(float(out["loss"])) and math.isfinite(float(out["flow_loss"])) and math.isfinite(float(out["l1"]))
     assert math.isfinite(float(out["grad_norm"])), "non-finite gradient norm after unscale_"
+    # n_gru_layers == 1 (config/stereo_human_config.py:38): the 1/16 and 1/32 GRUs and their context heads exist but are
+    # never called, upstream as here -- every other parameter must have received a finite gradient
     n_none = [n for n, p in st.model.named_parameters() if p.grad is None]
-    assert not n_none, n_none[:5]
-    assert all(bool(torch.isfinite(p.grad).all()) for p in st.model.parameters())
+    assert all(("gru16" in n or "gru32" in n or "outputs16" in n or "outputs32" in n or "layer4" in n or "layer5" in n)
+               for n in n_none), [n for n in n_none][:8]
+    with_grad = [p for p in st.model.parameters() if p.grad is not None]
+    assert sum(p.numel() for p in with_grad) > 2_000_000
+    assert all(bool(torch.isfinite(p.grad).all()) for p in with_grad)
     assert out["scale_after"] >= out["scale_before"], "GradScaler skipped the step (inf/nan gradients)"
     # gradients reached the Gaussian-parameter heads and the stereo update block through the rasterizer / sampler
     gp = st.model.gs_parm_regresser
     for head in (gp.rot_head, gp.scale_head, gp.opacity_head):
         assert float(sum(p.grad.abs().sum() for p in head.parameters())) > 0
-    assert float(sum(p.grad.abs().sum() for p in st.model.raft_stereo.update_module.parameters())) > 0
+    assert float(sum(p.grad.abs().sum() for p in st.model.raft_stereo.update_module.parameters() if p.grad is not None)) > 0
     # (b)
     img_pred = out["data"]["novel_view"]["img_pred"]
     assert tuple(img_pred.shape) == (2, 3, 2 * RES, 2 * RES)
@@ -116,7 +121,7 @@ def test_c3_flow_reg_cuda_equals_reg(dataset):
     mag = float(a.abs().max())
     print(f"flow after 3 iters: max|reg|={mag:.3f}px, max|reg - reg_cuda|={err:.3e}px, flow_loss {flows['reg'][1]:.4f} vs {flows['reg_cuda'][1]:.4f}")
     # fp16 volume (half ulp 2^-11 relative on correlations of O(1..10)) fed through 3 GRU iterations and x8 upsampling
-    assert err < 2e-2 * max(1.0, mag), (err, mag)
+    assert err < 5e-3 * max(1.0, mag), (err, mag)                       # measured on B200: 1.5e-3 px on a 3.9 px field
     assert abs(flows["reg"][1] - flows["reg_cuda"][1]) < 1e-2 * max(1.0, abs(flows["reg"][1]))
 
 
@@ -134,7 +139,7 @@ def test_c3_patched_fast_paths_give_the_same_step(dataset):
             assert core.raft_stereo_human.CorrBlockFast1D.__module__.startswith(want)
             assert lib.GaussianRender.pts2render.__module__.startswith("gps_gaussian_b200" if mode == "patched" else "lib.")
             out = harness.c3_step(st, st.batch(0), pts2render=lib.GaussianRender.pts2render)
-            grads = torch.cat([p.grad.reshape(-1) for p in st.model.parameters()]).double()
+            grads = torch.cat([p.grad.reshape(-1) for p in st.model.parameters() if p.grad is not None]).double()
             res[mode] = (out["data"]["novel_view"]["img_pred"].detach().clone(), float(out["loss"]), grads,
                          out["scale_after"] >= out["scale_before"])
         finally:
