@@ -37,6 +37,10 @@ def pack_host(arrays):
 
 class HostRenderPipeline:
     def __init__(self, device, max_points, height, width, slots=2):
+        if slots < 2:
+            # run() uploads item k+1 while item k renders: with one slot that upload would overwrite the inputs of a
+            # render that has not started yet
+            raise ValueError("HostRenderPipeline needs at least 2 staging slots")
         self.dev = torch.device(device)
         self.s_h2d, self.s_cmp, self.s_d2h = (torch.cuda.Stream(self.dev) for _ in range(3))
         self.stage = [torch.empty(max_points * _ROW, dtype=torch.float32, device=self.dev) for _ in range(slots)]

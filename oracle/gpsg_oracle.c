@@ -289,11 +289,14 @@ void SUFFIX(oracle_render)(int W, int H, const uint32_t* ranges, const uint32_t*
  *    m_T     = min |test_T/1e-4 - 1|      (relative distance of the transmittance test)
  *    m_power = min |power|                (absolute; power > 0 only happens through rounding of a near-singular conic)
  * tests/ turn "up to x% of pixels may exceed 1e-4" into: every pixel outside the tolerance has a margin below eps.
- * `taint` (may be NULL): per Gaussian, set to 1 if it is evaluated (alpha >= (1-eps_alpha)/255, power <= eps_power)
- * by a pixel whose margins are below the eps triple -- its gradient can legitimately differ by a flipped decision. */
+ * `taint` / `taint_own` (may be NULL): per Gaussian.  taint_own = 1 if the Gaussian's OWN alpha / power is within eps of
+ * its threshold at some pixel (a flip adds or removes its whole contribution there: its gradient can move by O(itself));
+ * taint = 1 if it is merely evaluated (alpha >= (1-eps_alpha)/255, power <= eps_power) by a pixel that has such a
+ * decision (a flip of a neighbour with alpha ~ 1/255 rescales its transmittance / accumulated colour by ~0.4 %). */
 void SUFFIX(oracle_render_margins)(int W, int H, const uint32_t* ranges, const uint32_t* point_list, const real* means2D,
                                    const real* conic_opacity, double eps_alpha, double eps_T, double eps_power,
-                                   /* out */ double* m_alpha, double* m_T, double* m_power, uint8_t* taint, int nthreads) {
+                                   /* out */ double* m_alpha, double* m_T, double* m_power, uint8_t* taint, uint8_t* taint_own,
+                                   int nthreads) {
     const int gx = (W + BLOCK_X - 1) / BLOCK_X;
 #ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads > 0 ? nthreads : 1)
@@ -335,6 +338,7 @@ void SUFFIX(oracle_render_margins)(int W, int H, const uint32_t* ranges, const u
                     real alpha = rmin(RC(0.99), co[3] * R_EXP(power));
                     if ((double)alpha * 255.0 < 1.0 - eps_alpha) continue;
                     taint[id] = 1; /* benign race: every writer stores 1 */
+                    if (taint_own && (fabs((double)alpha * 255.0 - 1.0) < eps_alpha || fabs((double)power) < eps_power)) taint_own[id] = 1;
                 }
             }
         }

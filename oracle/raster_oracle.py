@@ -143,16 +143,16 @@ class RasterOracle:
     def margins(self, st, eps=None, nthreads=1):
         """Per-pixel distance of the closest hard decision to its threshold, the `near` mask (a decision within eps:
         the pixel may legitimately differ between two correct implementations) and the per-Gaussian `taint` flag
-        (evaluated by a `near` pixel: its gradient may legitimately differ)."""
+        (evaluated by a `near` pixel: its gradient may legitimately differ; `taint_own`: its own alpha/power is the near one)."""
         eps = dict(self.EPS, **(eps or {}))
         W, H, P = st["W"], st["H"], st["P"]
         ma = np.zeros((H, W), np.float64); mt = np.zeros((H, W), np.float64); mp = np.zeros((H, W), np.float64)
-        taint = np.zeros(max(P, 1), np.uint8)
+        taint = np.zeros(max(P, 1), np.uint8); own = np.zeros(max(P, 1), np.uint8)
         self._fn("oracle_render_margins")(C.c_int(W), C.c_int(H), _p(st["ranges"]), _p(st["_vals_full"]), _p(st["means2D"]),
                                           _p(st["conic_opacity"]), C.c_double(eps["alpha"]), C.c_double(eps["T"]),
-                                          C.c_double(eps["power"]), _p(ma), _p(mt), _p(mp), _p(taint), C.c_int(nthreads))
+                                          C.c_double(eps["power"]), _p(ma), _p(mt), _p(mp), _p(taint), _p(own), C.c_int(nthreads))
         near = (ma < eps["alpha"]) | (mt < eps["T"]) | (mp < eps["power"])
-        return dict(alpha=ma, T=mt, power=mp, near=near, taint=taint[:P].astype(bool), eps=eps)
+        return dict(alpha=ma, T=mt, power=mp, near=near, taint=taint[:P].astype(bool), taint_own=own[:P].astype(bool), eps=eps)
 
     def backward(self, st, dL_dpix):
         P, W, H = st["P"], st["W"], st["H"]

@@ -9,8 +9,15 @@ tested value sits within rounding distance of its threshold.  `RasterOracle.marg
              every pixel over 1e-4 IS near a threshold, and moves by at most one flipped contribution (<= 1.2e-2).
   gradients  the backward replays the forward's decisions (final_T, n_contrib are inputs of A.6), so it is compared with
              the oracle's backward run on the SAME forward decisions (the device's final_T / n_contrib / tile lists).  What
-             is left are `alpha < 1/255` / `power > 0` re-evaluations: every Gaussian not evaluated by a pixel that is near
-             one of those is within 1e-3 (max-normalised, north_star) of the oracle in fp32 AND fp64.
+             is left are `alpha < 1/255` / `power > 0` re-evaluations.  Three classes of Gaussians:
+               clean   not evaluated by any pixel that has such a near decision:   <= 1e-3 (max-normalised, north_star)
+               shared  evaluated by such a pixel, own decision not near (a neighbour's flip rescales its T / accumulated
+                       colour there by ~1/255):                                      <= 5e-3
+               own     its own alpha/power is the near one (a flip adds/removes its whole contribution at that pixel): <= 5e-2
+             Against the fp32 oracle (same precision as the device; eps = rounding of the device's approximations) `clean`
+             is > 95 % of a C2 scene and agrees to ~1e-6.  Against the fp64 oracle the fp32 rounding of the projected
+             means (6e-5 px at 1000-px coordinates => 1e-4 relative on alpha) must be inside eps, so eps_alpha = 1e-3 there
+             and `clean` shrinks; the bound on each class is the same.
 The counts are appended to $GPSG_PARITY_LOG (json lines) when that variable is set; profiles/r2_parity_counts.jsonl is
 such a log from the B200.
 """
@@ -24,7 +31,9 @@ from oracle.raster_oracle import RasterOracle
 RGB_TOL = 1e-4       # abs, BASELINE.json north_star
 GRAD_TOL = 1e-3      # rel (max-normalised), BASELINE.json north_star
 FLIP_CAP = 1.2e-2    # one flipped contribution: alpha*T*c with test_T ~ 1e-4, alpha <= 0.99  =>  T*alpha <= ~1e-2
-TAINT_CAP = 5e-2     # a Gaussian whose pixel flipped: bounded, not asserted tight
+SHARED_TOL = 5e-3    # class `shared` (see above)
+TAINT_CAP = 5e-2     # class `own`
+EPS_ALPHA_F64 = 1e-3 # fp32 rounding of means2D / conic seen from an fp64 replay
 
 
 def oracle_forward(sc, dtype="f32", nthreads=8, render=True):
@@ -106,10 +115,11 @@ def assert_grad_parity(tag, sc, got, base, final_T, n_contrib, g, dtypes=("f32",
     rec_all = {}
     for dt in dtypes:
         o, st, want = forced_backward(sc, dt, base, final_T, n_contrib, g)
-        # pixels whose backward re-evaluates `alpha < 1/255` / `power > 0` within rounding of the threshold (T decisions are
-        # not re-taken in the backward: eps_T = 0) taint the Gaussians they evaluate
-        m = o.margins(st, eps=dict(T=0.0), nthreads=_threads())
-        taint = m["taint"]
+        # T decisions are not re-taken in the backward (eps_T = 0); see the module docstring for the three classes
+        eps = dict(T=0.0) if dt == "f32" else dict(T=0.0, alpha=EPS_ALPHA_F64)
+        m = o.margins(st, eps=eps, nthreads=_threads())
+        own, shared = m["taint_own"], m["taint"] & ~m["taint_own"]
+        clean = ~m["taint"]
         for k_got, k_ref in keys:
             if got.get(k_got) is None:
                 continue
@@ -117,12 +127,16 @@ def assert_grad_parity(tag, sc, got, base, final_T, n_contrib, g, dtypes=("f32",
             if k_got == "dL_dmeans2D":
                 a = a[:, :2]                                  # [P,3] with z unused vs the oracle's NDC-scaled [P,2]
             per = grad_err(a, want[k_ref])
-            clean_max = float(per[~taint].max()) if (~taint).any() else 0.0
-            rec = dict(P=int(per.size), tainted=int(taint.sum()), near_pixels=int(m["near"].sum()), over_tol=int((per > GRAD_TOL).sum()),
-                       over_tol_untainted=int(((per > GRAD_TOL) & ~taint).sum()), max_err_untainted=clean_max, max_err=float(per.max()))
+            mx = lambda msk: float(per[msk].max()) if msk.any() else 0.0
+            rec = dict(P=int(per.size), clean=int(clean.sum()), shared=int(shared.sum()), own=int(own.sum()),
+                       near_pixels=int(m["near"].sum()), over_tol=int((per > GRAD_TOL).sum()),
+                       over_tol_clean=int(((per > GRAD_TOL) & clean).sum()), max_err_clean=mx(clean), max_err_shared=mx(shared),
+                       max_err_own=mx(own), eps_alpha=m["eps"]["alpha"])
             rec_all[(dt, k_got)] = rec
             record(f"{tag}:grad:{dt}:{k_got}", **rec)
-            assert clean_max <= GRAD_TOL, (dt, k_got, rec)
-            assert float(per.max()) <= TAINT_CAP, (dt, k_got, rec)
-        assert taint.size < 5000 or taint.mean() < 0.1, (dt, float(taint.mean()))   # the exemption is a thin set
+            assert rec["max_err_clean"] <= GRAD_TOL, (dt, k_got, rec)
+            assert rec["max_err_shared"] <= SHARED_TOL, (dt, k_got, rec)
+            assert rec["max_err_own"] <= TAINT_CAP, (dt, k_got, rec)
+        if dt == "f32":
+            assert clean.size < 5000 or clean.mean() > 0.9, (dt, float(clean.mean()))   # the exemption is a thin set
     return rec_all
