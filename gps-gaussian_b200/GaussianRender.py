@@ -39,9 +39,13 @@ class _RasterizeMaps(torch.autograd.Function):
         xyz, img = [_f32(xl.detach()), _f32(xr.detach())], [_f32(il.detach()), _f32(ir_.detach())]
         rot, scale = [_f32(rl.detach()), _f32(rr.detach())], [_f32(sl.detach()), _f32(sr.detach())]
         opac = [_f32(ol.detach()), _f32(orr.detach())]
+        if valid[1].numel() != S2:
+            raise RuntimeError("pts2render (gpsg_sm100): lmain and rmain pts_valid differ in size")
         for t, n in ((xyz, 3), (img, 3), (rot, 4), (scale, 3), (opac, 1)):
             if any(u.numel() != n * S2 for u in t):
                 raise RuntimeError("pts2render (gpsg_sm100): map shapes do not match pts_valid")
+        if any(u.device != dev for t in (valid, xyz, img, rot, scale, opac) for u in t):
+            raise RuntimeError("pts2render (gpsg_sm100): all source-view maps must live on one CUDA device")
         H, W = int(settings.image_height), int(settings.image_width)
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((2 * S2,), dtype=torch.int32, device=dev)
@@ -97,11 +101,13 @@ def _settings(data, idx, bg_color):
     s.tanfovy = math.tan(float(nv['FovY'][idx]) * 0.5)
     s.bg[:] = [float(v) for v in bg_color]
     s.scale_modifier = 1.0
-    host = lambda t, n: t.detach().to('cpu', torch.float32).reshape(-1).tolist()[:n]
-    s.viewmatrix[:] = host(nv['world_view_transform'][idx], 16)
-    s.projmatrix[:] = host(nv['full_proj_transform'][idx], 16)
+    # at most one device->host transfer for the 35 camera floats (CUDA in the test scripts, host in training)
+    cam = torch.cat([nv['world_view_transform'][idx].detach().reshape(-1).float(), nv['full_proj_transform'][idx].detach().reshape(-1).float(),
+                     nv['camera_center'][idx].detach().reshape(-1).float()]).cpu().tolist()
+    s.viewmatrix[:] = cam[0:16]
+    s.projmatrix[:] = cam[16:32]
     s.sh_degree = 3
-    s.campos[:] = host(nv['camera_center'][idx], 3)
+    s.campos[:] = cam[32:35]
     s.prefiltered, s.debug = 0, 0
     return s
 

@@ -104,6 +104,7 @@ static ImageState carve_image(char* p, int W, int H, char** end) {
     im.totals = take<uint32_t>(p, 64);            // directly after tile_count: one memset clears both
     im.tile_cursor = take<uint32_t>(p, tiles > 0 ? tiles : 1);
     im.big_tiles = take<uint32_t>(p, tiles > 0 ? tiles : 1);
+    im.tile_order = take<uint32_t>(p, tiles > 0 ? tiles : 1);
     if (end) *end = p;
     return im;
 }
@@ -390,7 +391,7 @@ int gpsg_rasterize_forward_maps_planned(const GpsgRasterSettings* s, int device,
 
 size_t gpsg_rasterize_backward_workspace_bytes(int P) {
     const size_t n = (size_t)(P > 0 ? P : 1);
-    return align_up(sizeof(float4) * n) + align_up(sizeof(float) * 3 * n) + 256;   // dL_dconic+opacity, dL_dcolors (SH path)
+    return align_up(sizeof(float4) * 3 * n) + align_up(sizeof(float) * 3 * n) + 256;   // packed accumulator rows, dL_dcolors (SH path)
 }
 
 static int backward_common(const GpsgRasterSettings* s, int device, cudaStream_t stream, int P, int sh_M,
@@ -403,18 +404,18 @@ static int backward_common(const GpsgRasterSettings* s, int device, cudaStream_t
     BinningState b = BinningState::carve(const_cast<void*>(binning_buffer), (size_t)num_rendered, 0);
     ImageState im = ImageState::carve(const_cast<void*>(image_buffer), cam.W, cam.H);
     GeomState gst = GeomState::carve(const_cast<void*>(geom_buffer), P, 0);
-    float4* dconic_op = (float4*)align_up((size_t)workspace);
-    if (!dL_dcolors) dL_dcolors = (float*)((char*)dconic_op + align_up(sizeof(float4) * (size_t)P));   // scratch
-    GPSG_CUDA(cudaMemsetAsync(dL_dmeans2D, 0, sizeof(float) * 3 * (size_t)P, stream));
-    GPSG_CUDA(cudaMemsetAsync(dL_dcolors, 0, sizeof(float) * 3 * (size_t)P, stream));
-    GPSG_CUDA(cudaMemsetAsync(dconic_op, 0, sizeof(float4) * (size_t)P, stream));
+    // one packed accumulator row (3 x float4) per Gaussian: the only buffer that needs zeroing -- the projection backward
+    // writes d/dmeans2D and d/dcolours for every Gaussian
+    float4* grad_acc = (float4*)align_up((size_t)workspace);
+    if (!dL_dcolors && shs) dL_dcolors = (float*)((char*)grad_acc + align_up(sizeof(float4) * 3 * (size_t)P));   // SH path scratch
+    GPSG_CUDA(cudaMemsetAsync(grad_acc, 0, sizeof(float4) * 3 * (size_t)P, stream));
     int rc = GPSG_OK;
     if (num_rendered > 0) {
-        { StageTimer t(ST_RENDER_BWD, stream, 1); rc = launch_render_backward(cam, b, im, dL_dout_color, dL_dmeans2D, dconic_op, dL_dcolors, stream); }
+        { StageTimer t(ST_RENDER_BWD, stream, 1); rc = launch_render_backward(cam, b, im, dL_dout_color, grad_acc, stream); }
         if (rc) return rc;
     }
     { StageTimer t(ST_PREPROCESS_BWD, stream, 1);
-      rc = launch_preprocess_backward(cam, P, src, radii, gst.conic_opacity, dL_dmeans2D, dconic_op, dL_dcolors, out, stream); }
+      rc = launch_preprocess_backward(cam, P, src, radii, gst.conic_opacity, grad_acc, dL_dmeans2D, dL_dcolors, out, stream); }
     if (rc) return rc;
     if (shs) {
         rc = launch_sh_backward(P, s->sh_degree, sh_M, s->campos, src.means3D, shs, radii, gst.clamped, dL_dcolors, dL_dsh,
@@ -463,7 +464,7 @@ int gpsg_rasterize_backward(const GpsgRasterSettings* s, int device, void* strea
 
 size_t gpsg_rasterize_backward_maps_workspace_bytes(int pixels_per_view) {
     const size_t n = (size_t)(pixels_per_view > 0 ? 2 * pixels_per_view : 1);
-    return align_up(sizeof(float4) * n) + align_up(sizeof(float) * 3 * n) + align_up(sizeof(float) * 3 * n) + 512;
+    return align_up(sizeof(float4) * 3 * n) + align_up(sizeof(float) * 3 * n) + 512;     // accumulator rows + dL_dmeans2D
 }
 
 int gpsg_rasterize_backward_maps(const GpsgRasterSettings* s, int device, void* stream_, int pixels_per_view,
@@ -487,9 +488,9 @@ int gpsg_rasterize_backward_maps(const GpsgRasterSettings* s, int device, void* 
         out.dopac[v] = dL_dopacity[v];
     }
     const int P = 2 * pixels_per_view;
-    // workspace: [float4 P moments][float 3P dL_dcolors][float 3P dL_dmeans2D]
+    // workspace: [3 x float4 P accumulator rows][float 3P dL_dmeans2D]
     char* w = (char*)align_up((size_t)workspace);
-    float* dmeans2D = (float*)(w + align_up(sizeof(float4) * (size_t)P) + align_up(sizeof(float) * 3 * (size_t)P));
+    float* dmeans2D = (float*)(w + align_up(sizeof(float4) * 3 * (size_t)P));
     return backward_common(s, device, (cudaStream_t)stream_, P, 0, num_rendered,
                            maps_src(pixels_per_view, valid, xyz, img, rot, scale, opacity), nullptr, radii, geom_buffer,
                            binning_buffer, image_buffer, dL_dout_color, dmeans2D, nullptr, nullptr, out, workspace);

@@ -129,6 +129,7 @@ struct ImageState {
     uint32_t* tile_cursor;// [tiles]  scatter cursors
     uint32_t* totals;     // [64]     N, max count, overflow flag, #big tiles, preprocess CTA ticket (see tile_scan.cuh)
     uint32_t* big_tiles;  // [tiles]  ids of tiles with more than kBigTile pairs
+    uint32_t* tile_order; // [tiles]  all tile ids, longest list first (tile_scan.cuh): work order of the compositing kernels
     static size_t required(int W, int H);
     static ImageState carve(void* base, int W, int H);
 };
@@ -156,13 +157,13 @@ int launch_tile_sort_gather(const Camera& cam, int P, uint32_t max_count, const 
 // raster_render.cu
 int launch_render_forward(const Camera& cam, BinningState b, ImageState im, float* out_color, cudaStream_t stream);
 // raster_backward.cu
-int launch_render_backward(const Camera& cam, BinningState b, ImageState im, const float* dL_dpix,
-                           float* dL_dmeans2D /*[P,3]*/, float4* dL_dconic_op /*[P] (x,y,w,opacity)*/,
-                           float* dL_dcolors /*[P,3]*/, cudaStream_t stream);
+// grad_acc: [P] rows of 3 x float4 (12 floats, zero-initialised by the caller) -- the packed accumulator of the
+// compositing backward: (S s dx, S s dy, S s dx^2, S s dx dy | S s dy^2, S s, S w g_r, S w g_g | S w g_b, -, -, -)
+int launch_render_backward(const Camera& cam, BinningState b, ImageState im, const float* dL_dpix, float4* grad_acc,
+                           cudaStream_t stream);
 int launch_preprocess_backward(const Camera& cam, int P, const GaussianSrc& src, const int32_t* radii,
-                               const float4* conic_opacity, float* dL_dmeans2D /* in: moments, out: gradient */,
-                               const float4* dL_dconic_op /* moments */, const float* dL_dcolors,
-                               const GaussianGrads& out, cudaStream_t stream);
+                               const float4* conic_opacity, const float4* grad_acc, float* dL_dmeans2D /* out [P,3] */,
+                               float* dL_dcolors /* out [P,3] or NULL */, const GaussianGrads& out, cudaStream_t stream);
 // sh.cu
 int launch_sh_forward(int P, int deg, int M, const float* campos3, const float* means3D, const float* shs,
                       const int32_t* radii, float* rgb, uint8_t* clamped, cudaStream_t stream);

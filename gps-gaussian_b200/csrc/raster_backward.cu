@@ -4,8 +4,6 @@
 #include "gpsg_internal.cuh"
 #include "slab_ring.cuh"
 
-#include <cstdlib>
-#include <cstring>
 
 namespace gpsg {
 
@@ -13,195 +11,25 @@ constexpr int kBwdChunk = 64;   // Gaussians per ring stage
 constexpr int kBwdStages = 8;
 constexpr int kBwdWarps = 4;    // consumer warps per CTA: 16 x 8 pixels (half a tile)
 
-// One butterfly exchange step of a reduce-scatter: halves the number of live values per lane.
-// Lanes whose `bit` is set keep the upper half, the others the lower half; out[i] = kept[i] + partner's copy.
-template <int N>
-__device__ __forceinline__ void rs_step(float* x, int lane, int bit) {
-    const bool up = (lane & bit) != 0;
-#pragma unroll
-    for (int i = 0; i < N / 2; ++i) {
-        const float send = up ? x[i] : x[i + N / 2];
-        const float keep = up ? x[i + N / 2] : x[i];
-        x[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-    }
-}
-
-// A.6: per (half) tile, pixels replay their list back to front.
-//  * slabs streamed by the producer lane's TMA bulk copies into the shared-memory ring (slab_ring.cuh), starting
-//    at the deepest contributor of the CTA; consumer warps never block on each other;
-//  * the same warp-level bounding-box culling as the forward, plus skipping everything behind the warp's deepest
-//    contributor;
-//  * per-pixel gradient terms of TWO surviving Gaussians (18 values) are reduced across the warp with a butterfly
-//    reduce-scatter (21 shuffles instead of 90), leaving one total per lane, then one global RED per value
-//    (fp32 shared-memory atomics are CAS loops on sm_100a; global REDs are native).
-__global__ void __launch_bounds__((kBwdWarps + 1) * 32) render_backward_kernel(const __grid_constant__ Camera cam,
-                                                                             const float4* __restrict__ slabA,
-                                                                             const float4* __restrict__ slabB,
-                                                                             const float4* __restrict__ slabC,
-                                                                             const uint2* __restrict__ ranges, const uint32_t* __restrict__ status,
-                                                                             const float* __restrict__ final_T,
-                                                                             const uint32_t* __restrict__ n_contrib,
-                                                                             const float* __restrict__ dL_dpix,
-                                                                             float* __restrict__ dL_dmeans2D,
-                                                                             float4* __restrict__ dL_dconic_op,
-                                                                             float* __restrict__ dL_dcolors) {
-    __shared__ SlabRing<kBwdChunk, kBwdStages> ring;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile_y = blockIdx.y >> 1, half = blockIdx.y & 1;
-    const int tile = tile_y * cam.grid_x + blockIdx.x;
-    const uint2 range = status[2] ? make_uint2(0u, 0u) : ranges[tile];   // planned-mode overflow: render nothing
-    const int total = (int)(range.y - range.x);
-
-    // per-pixel state (consumer warps only; the producer warp's lanes map outside and stay inert)
-    const int bx0 = blockIdx.x * GPSG_TILE_X + ((warp & 1) << 3);
-    const int by0 = tile_y * GPSG_TILE_Y + (half << 3) + ((warp >> 1) << 2);
-    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
-    const bool inside = warp < kBwdWarps && px < cam.W && py < cam.H;
-    const float pixfx = (float)px, pixfy = (float)py;
-    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
-    const size_t HW = (size_t)cam.W * cam.H;
-    const size_t pid = (size_t)py * cam.W + px;
-    const float T_final = inside ? final_T[pid] : 0.0f;
-    const int last_contributor = inside ? (int)n_contrib[pid] : 0;
-    const int wmax = __reduce_max_sync(0xffffffffu, last_contributor);  // positions >= wmax: nothing to do for this warp
-
-    if (tid == 0) ring_init(ring, kBwdWarps);
-    __syncthreads();
-    if (lane == 0 && wmax > 0) atomicMax(&ring.hi, wmax);
-    __syncthreads();
-    const int hi = min(total, *(volatile int*)&ring.hi);  // only list positions [0, hi) matter for this CTA
-    const int nbatch = (hi + kBwdChunk - 1) / kBwdChunk;
-    // batch b = positions [end - n, end), end = hi - b*chunk  (back to front)
-
-    if (warp == kBwdWarps) {  // ---------------- producer warp ----------------
-        if (lane == 0)
-            ring_produce(ring, nbatch, kBwdWarps, slabA, slabB, slabC,
-                         [&](int b) { const int end = hi - b * kBwdChunk; return (size_t)range.x + (size_t)(end - min(kBwdChunk, end)); },
-                         [&](int b) { return min(kBwdChunk, hi - b * kBwdChunk); });
-        return;
-    }
-
-    float T = T_final;
-    float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f, lastc0 = 0.f, lastc1 = 0.f, lastc2 = 0.f, last_alpha = 0.f;
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-    if (inside) { g0 = dL_dpix[pid]; g1 = dL_dpix[HW + pid]; g2 = dL_dpix[2 * HW + pid]; }
-    const float bg_dot = (cam.bg[0] * g0 + cam.bg[1] * g1) + cam.bg[2] * g2;
-    const float ddelx_dx = 0.5f * (float)cam.W, ddely_dy = 0.5f * (float)cam.H;
-
-    for (int b = 0; b < nbatch; ++b) {
-        ring_wait_full(ring, b, kBwdWarps + 1 /* never "all done" in the backward */);
-        const int s = b % kBwdStages;
-        const int end = hi - b * kBwdChunk;
-        const int n = min(kBwdChunk, end);
-        const int start = end - n;
-        if (start < wmax) {
-            const float4* __restrict__ SA = ring.A[s];
-            const float4* __restrict__ SB = ring.B[s];
-            const float4* __restrict__ SC = ring.C[s];
-            // Survivors are taken two at a time (deeper one first): their 2 x 9 per-pixel gradient terms go straight
-            // into x[0..7]/x[8..15] (dmx,dmy,dcx,dcy,dcw,dop,dr,dg) and y[0..1] (db), then one butterfly per pair.
-            // Straight-line, predicated evaluation (as in the forward): the gradient tail runs whenever any lane is
-            // active, so per-lane branches would only add BSSY/BSYNC/BRA and register shuffling at the merge points.
-            auto eval = [&](int j, bool enable, float* xo, float& yo) -> bool {
-                const float2 xy = *reinterpret_cast<const float2*>(&SA[j]);
-                const float4 q = SB[j];
-                const float4 c = SC[j];
-                const float dx = xy.x - pixfx, dy = xy.y - pixfy;
-                const float p = fmaf(q.z * dy, dy, fmaf(q.x, dx, q.y * dy) * dx);   // log2e * power
-                const float G = ex2_approx(p);
-                const float alpha = fminf(0.99f, q.w * G);
-                const bool active = enable && (start + j) < last_contributor && !(p > 0.0f) && !(alpha < 1.0f / 255.0f);
-                const float inv1ma = __frcp_rn(1.0f - alpha);
-                const float Tn = T * inv1ma;
-                const float a0 = fmaf(last_alpha, lastc0 - accum0, accum0);
-                const float a1 = fmaf(last_alpha, lastc1 - accum1, accum1);
-                const float a2 = fmaf(last_alpha, lastc2 - accum2, accum2);
-                float dL_dalpha = (c.x - a0) * g0;
-                dL_dalpha = fmaf(c.y - a1, g1, dL_dalpha);
-                dL_dalpha = fmaf(c.z - a2, g2, dL_dalpha);
-                dL_dalpha = fmaf(dL_dalpha, Tn, (-T_final * inv1ma) * bg_dot);
-                // Raw moments of s = G * dL/dG over the pixels (converted to d/dmean2D, d/dconic, d/dopacity once
-                // per Gaussian in preprocess_backward):  xo[0..5] = s * (dx, dy, dx^2, dx*dy, dy^2, 1)
-                const float sG = active ? G * (q.w * dL_dalpha) : 0.0f;
-                const float dch = active ? alpha * Tn : 0.0f;
-                const float sx = sG * dx, sy = sG * dy;
-                xo[0] = sx;
-                xo[1] = sy;
-                xo[2] = sx * dx;
-                xo[3] = sx * dy;
-                xo[4] = sy * dy;
-                xo[5] = sG;
-                xo[6] = dch * g0;
-                xo[7] = dch * g1;
-                yo = dch * g2;
-                T = active ? Tn : T;
-                accum0 = active ? a0 : accum0; accum1 = active ? a1 : accum1; accum2 = active ? a2 : accum2;
-                lastc0 = active ? c.x : lastc0; lastc1 = active ? c.y : lastc1; lastc2 = active ? c.z : lastc2;
-                last_alpha = active ? alpha : last_alpha;
-                return active;
-            };
-            for (int base = ((n - 1) >> 5) << 5; base >= 0; base -= 32) {
-                if (start + base >= wmax) continue;
-                const int my = base + lane;
-                bool hit = false;
-                if (my < n && start + my < wmax) {
-                    const float4 a = SA[my];
-                    hit = (a.x >= wx0 - a.z) && (a.x <= wx1 + a.z) && (a.y >= wy0 - a.w) && (a.y <= wy1 + a.w);
-                }
-                unsigned m = __ballot_sync(0xffffffffu, hit);
-                while (m) {
-                    float x[16], y[2];
-                    const int bitA = 31 - __clz(m);
-                    m &= ~(1u << bitA);
-                    const bool two = m != 0;
-                    const int bitB = two ? 31 - __clz(m) : bitA;
-                    m &= ~(two ? (1u << bitB) : 0u);
-                    const int jA = base + bitA, jB = base + bitB;
-                    bool act = eval(jA, true, x, y[0]);
-                    act |= eval(jB, two, x + 8, y[1]);        // disabled second slot contributes exact zeros
-                    if (!__any_sync(0xffffffffu, act)) continue;
-                    rs_step<16>(x, lane, 16);
-                    rs_step<8>(x, lane, 8);
-                    rs_step<4>(x, lane, 4);
-                    rs_step<2>(x, lane, 2);
-                    const float tot = x[0] + __shfl_xor_sync(0xffffffffu, x[0], 1);  // lane l holds total of value l>>1
-                    rs_step<2>(y, lane, 16);
-                    float tb = y[0];
-                    tb += __shfl_xor_sync(0xffffffffu, tb, 8);
-                    tb += __shfl_xor_sync(0xffffffffu, tb, 4);
-                    tb += __shfl_xor_sync(0xffffffffu, tb, 2);
-                    tb += __shfl_xor_sync(0xffffffffu, tb, 1);                       // lanes 0-15: first, 16-31: second
-                    const int gsel = lane >> 4;
-                    if (gsel == 0 || two) {
-                        const uint32_t id = __float_as_uint(SC[gsel ? jB : jA].w);
-                        if ((lane & 1) == 0 && tot != 0.0f) {
-                            const int k = (lane >> 1) & 7;
-                            float* dst = (k < 2) ? (dL_dmeans2D + 3 * (size_t)id + k)
-                                                 : (k < 6) ? (reinterpret_cast<float*>(dL_dconic_op + id) + (k - 2))
-                                                           : (dL_dcolors + 3 * (size_t)id + (k - 6));
-                            atomicAdd(dst, tot);
-                        }
-                        if ((lane & 15) == 1 && tb != 0.0f) atomicAdd(dL_dcolors + 3 * (size_t)id + 2, tb);
-                    }
-                }
-            }
-        }
-        ring_release(ring, b, lane);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
-// A.6, second formulation: pixel-major replay + GAUSSIAN-major reduction.
-// The butterfly above spends ~2/3 of its instructions reducing 9 per-pixel products per survivor across the warp.  Here the
+// A.6: pixel-major replay + GAUSSIAN-major reduction.
+// (A first formulation reduced the 9 per-pixel products of every survivor across the warp with a butterfly reduce-scatter and
+// spent ~2/3 of its instructions doing so: 443 us at C2 against 304 us for this one -- removed in round 2.)  Here the
 // sequential part (per pixel, back to front: alpha, T, the running colour) only produces the two scalars every gradient
 // term is linear in,  s = G * opacity * dL/dalpha  and  w = alpha * T,  and parks them in shared memory, one row of 32 pixels
 // per surviving Gaussian.  Once kQ = 16 rows are parked the roles flip: lane (j, h) owns Gaussian j and pixel rows
 // [2h, 2h+1] of the warp's 8x4 block, walks its 16 pixels accumulating the 9 sums
 //   sum s*dx, s*dy, s*dx^2, s*dx*dy, s*dy^2, s   and   sum w*g_r, w*g_g, w*g_b
-// in registers -- no shuffles -- then the two halves are added with one shuffle per value and each lane issues the global
-// REDs of its Gaussian.  Rows are padded to 33 floats: conflict-free both when a pixel-lane writes column `lane` of row
-// `slot` and when Gaussian-lanes read `row j, column p`.
+// in registers -- no shuffles -- then the two halves are added with one shuffle per value and the sums leave the SM as
+// 128-bit vector reductions (`REDG.E.ADD.F32x4`, sm_90+) into a packed per-Gaussian accumulator row of 12 floats
+//   acc[id] = { (S s dx, S s dy, S s dx^2, S s dx dy), (S s dy^2, S s, S w g_r, S w g_g), (S w g_b, -, -, -) }:
+// one v4 RED from the lower half-warp, one v4 + one scalar RED from the upper -- 3 L2 reduction sectors per (warp,
+// Gaussian) instead of 9 (ncu r1: 16.4 M RED sectors = 526 MB of L2 traffic against 47 MB algorithmic).
+// Rows are padded to 33 floats: conflict-free both when a pixel-lane writes column `lane` of row `slot` and when
+// Gaussian-lanes read `row j, column p`.
+// The per-pixel replay is branch-free in its state: an inactive (pixel, Gaussian) pair is replayed with G = 0, hence
+// alpha = 0, 1/(1-alpha) = 1, w = s = 0; folding (last_alpha, last_colour) into the running colour one step early and
+// then carrying alpha = 0 gives bit-identical state to skipping the pair, with ONE select instead of eight.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kQ = 16;
 struct __align__(16) BwdWarpBuf {
@@ -218,23 +46,22 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32, MIN_BLOCKS) render_backw
                                                                                 const float4* __restrict__ slabA,
                                                                                 const float4* __restrict__ slabB,
                                                                                 const float4* __restrict__ slabC,
-                                                                                const uint2* __restrict__ ranges, const uint32_t* __restrict__ status,
+                                                                                const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
+                                                                                const uint32_t* __restrict__ status,
                                                                                 const float* __restrict__ final_T,
                                                                                 const uint32_t* __restrict__ n_contrib,
                                                                                 const float* __restrict__ dL_dpix,
-                                                                                float* __restrict__ dL_dmeans2D,
-                                                                                float4* __restrict__ dL_dconic_op,
-                                                                                float* __restrict__ dL_dcolors) {
+                                                                                float4* __restrict__ grad_acc) {
     __shared__ SlabRing<kBwdChunk, STAGES> ring;
     __shared__ BwdWarpBuf wbuf[kBwdWarps];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile_y = blockIdx.y >> 1, half = blockIdx.y & 1;
-    const int tile = tile_y * cam.grid_x + blockIdx.x;
+    const int tile = (int)tile_order[blockIdx.x >> 1], half = blockIdx.x & 1;      // longest tile lists first (tile_scan.cuh)
+    const int tile_y = tile / cam.grid_x, tile_x = tile - tile_y * cam.grid_x;
     const uint2 range = status[2] ? make_uint2(0u, 0u) : ranges[tile];   // planned-mode overflow: render nothing
     const int total = (int)(range.y - range.x);
 
-    const int bx0 = blockIdx.x * GPSG_TILE_X + ((warp & 1) << 3);
+    const int bx0 = tile_x * GPSG_TILE_X + ((warp & 1) << 3);
     const int by0 = tile_y * GPSG_TILE_Y + (half << 3) + ((warp >> 1) << 2);
     const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
     const bool inside = warp < kBwdWarps && px < cam.W && py < cam.H;
@@ -311,18 +138,12 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32, MIN_BLOCKS) render_backw
         c2 += __shfl_xor_sync(0xffffffffu, c2, 16);
         if (on) {
             const uint32_t id = __float_as_uint(me.z);
-            float* cop = reinterpret_cast<float*>(dL_dconic_op + id);
-            if (qh == 0) {      // lower half of the warp: mean + three conic moments
-                if (m0 != 0.f) atomicAdd(dL_dmeans2D + 3 * (size_t)id, m0);
-                if (m1 != 0.f) atomicAdd(dL_dmeans2D + 3 * (size_t)id + 1, m1);
-                if (k0 != 0.f) atomicAdd(cop, k0);
-                if (k1 != 0.f) atomicAdd(cop + 1, k1);
-                if (k2 != 0.f) atomicAdd(cop + 2, k2);
-            } else {            // upper half: opacity moment + colour
-                if (k3 != 0.f) atomicAdd(cop + 3, k3);
-                if (c0 != 0.f) atomicAdd(dL_dcolors + 3 * (size_t)id, c0);
-                if (c1 != 0.f) atomicAdd(dL_dcolors + 3 * (size_t)id + 1, c1);
-                if (c2 != 0.f) atomicAdd(dL_dcolors + 3 * (size_t)id + 2, c2);
+            float4* acc = grad_acc + 3 * (size_t)id;
+            if (qh == 0) {      // lower half of the warp: mean moments + two conic moments
+                if (m0 != 0.f || m1 != 0.f || k0 != 0.f || k1 != 0.f) atomicAdd(acc, make_float4(m0, m1, k0, k1));
+            } else {            // upper half: third conic moment, opacity moment, colour
+                if (k2 != 0.f || k3 != 0.f || c0 != 0.f || c1 != 0.f) atomicAdd(acc + 1, make_float4(k2, k3, c0, c1));
+                if (c2 != 0.f) atomicAdd(reinterpret_cast<float*>(acc + 2), c2);
             }
         }
         __syncwarp();
@@ -360,23 +181,24 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32, MIN_BLOCKS) render_backw
                     const float alpha = fminf(0.99f, q.w * G);
                     const bool active = (start + j) < last_contributor && !(p > 0.0f) && !(alpha < 1.0f / 255.0f);
                     if (!__any_sync(0xffffffffu, active)) continue;
+                    // inactive pairs are replayed with G = 0 (see the header): alpha_e = 0, inv1ma = 1, s = w = 0
+                    const float Ge = active ? G : 0.0f;
+                    const float alpha_e = fminf(0.99f, q.w * Ge);
                     float inv1ma;                                 // 1 - alpha >= 0.01: MUFU.RCP (1 ulp) without the slow path
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1ma) : "f"(1.0f - alpha));
-                    const float Tn = T * inv1ma;
-                    const float a0 = fmaf(last_alpha, lastc0 - accum0, accum0);
-                    const float a1 = fmaf(last_alpha, lastc1 - accum1, accum1);
-                    const float a2 = fmaf(last_alpha, lastc2 - accum2, accum2);
-                    float dL_dalpha = (c.x - a0) * g0;
-                    dL_dalpha = fmaf(c.y - a1, g1, dL_dalpha);
-                    dL_dalpha = fmaf(c.z - a2, g2, dL_dalpha);
-                    dL_dalpha = fmaf(dL_dalpha, Tn, (-T_final * inv1ma) * bg_dot);
-                    wb.S[slot][lane] = active ? G * (q.w * dL_dalpha) : 0.0f;
-                    wb.Wt[slot][lane] = active ? alpha * Tn : 0.0f;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1ma) : "f"(1.0f - alpha_e));
+                    T *= inv1ma;
+                    accum0 = fmaf(last_alpha, lastc0 - accum0, accum0);
+                    accum1 = fmaf(last_alpha, lastc1 - accum1, accum1);
+                    accum2 = fmaf(last_alpha, lastc2 - accum2, accum2);
+                    float dL_dalpha = (c.x - accum0) * g0;
+                    dL_dalpha = fmaf(c.y - accum1, g1, dL_dalpha);
+                    dL_dalpha = fmaf(c.z - accum2, g2, dL_dalpha);
+                    dL_dalpha = fmaf(dL_dalpha, T, (-T_final * inv1ma) * bg_dot);
+                    wb.S[slot][lane] = Ge * (q.w * dL_dalpha);
+                    wb.Wt[slot][lane] = alpha_e * T;
                     if (lane == 0) wb.meta[slot] = make_float4(xy.x, xy.y, c.w, 0.f);
-                    T = active ? Tn : T;
-                    accum0 = active ? a0 : accum0; accum1 = active ? a1 : accum1; accum2 = active ? a2 : accum2;
-                    lastc0 = active ? c.x : lastc0; lastc1 = active ? c.y : lastc1; lastc2 = active ? c.z : lastc2;
-                    last_alpha = active ? alpha : last_alpha;
+                    lastc0 = c.x; lastc1 = c.y; lastc2 = c.z;
+                    last_alpha = alpha_e;
                     if (++slot == kQ) { flush(kQ); slot = 0; }
                 }
             }
@@ -386,18 +208,12 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32, MIN_BLOCKS) render_backw
     if (slot > 0) flush(slot);
 }
 
-int launch_render_backward(const Camera& cam, BinningState b, ImageState im, const float* dL_dpix, float* dL_dmeans2D,
-                           float4* dL_dconic_op, float* dL_dcolors, cudaStream_t stream) {
-    dim3 grid(cam.grid_x, cam.grid_y * 2);
-    const char* e = getenv("GPSG_BWD");                       // "butterfly" selects the first formulation
-    if (e && strcmp(e, "butterfly") == 0)
-        render_backward_kernel<<<grid, (kBwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges, im.totals,
-                                                                         im.final_T, im.n_contrib, dL_dpix, dL_dmeans2D,
-                                                                         dL_dconic_op, dL_dcolors);
-    else
-        render_backward_gm_kernel<8, 5><<<grid, (kBwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges,
-                                                                                  im.totals, im.final_T, im.n_contrib, dL_dpix,
-                                                                                  dL_dmeans2D, dL_dconic_op, dL_dcolors);
+int launch_render_backward(const Camera& cam, BinningState b, ImageState im, const float* dL_dpix, float4* grad_acc,
+                           cudaStream_t stream) {
+    const unsigned grid = 2u * (unsigned)(cam.grid_x * cam.grid_y);
+    render_backward_gm_kernel<8, 5><<<grid, (kBwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges,
+                                                                              im.tile_order, im.totals, im.final_T, im.n_contrib, dL_dpix,
+                                                                              grad_acc);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
 }
@@ -405,13 +221,16 @@ int launch_render_backward(const Camera& cam, BinningState b, ImageState im, con
 // A.7 + A.8 fused: per Gaussian, (dL/dmean2D, dL/dconic) -> dL/d{mean3D, cov3D, scale, rotation}.
 __global__ void __launch_bounds__(256) preprocess_backward_kernel(
     const __grid_constant__ Camera cam, int P, const GaussianSrc src, const int32_t* __restrict__ radii,
-    const float4* __restrict__ conic_opacity, const float* dL_dmeans2D, float* dL_dmeans2D_out,
-    const float4* __restrict__ dL_dconic_op, const float* __restrict__ dL_dcolors, const GaussianGrads out) {
+    const float4* __restrict__ conic_opacity, const float4* __restrict__ grad_acc, float* __restrict__ dL_dmeans2D_out,
+    float* __restrict__ dL_dcolors_out, const GaussianGrads out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     float dm[3] = {0.f, 0.f, 0.f}, dsc[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float dop = 0.f, dm2[2] = {0.f, 0.f};
+    // packed accumulator row of the compositing backward (see render_backward_gm_kernel)
+    const float4 acc0 = grad_acc[3 * (size_t)i], acc1 = grad_acc[3 * (size_t)i + 1];
+    const float dcol[3] = {acc1.z, acc1.w, reinterpret_cast<const float*>(grad_acc + 3 * (size_t)i + 2)[0]};
     if (radii[i] > 0) {
         const float* view = cam.view;
         const float* proj = cam.proj;
@@ -419,12 +238,12 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
         float4 qin = make_float4(0.f, 0.f, 0.f, 0.f);
         src_geom(src, i, x, y, z, sc3, qin, opac_in);            // radii > 0 implies a valid Gaussian
         const float* cov3D_precomp = src.cov3D_precomp;
-        // The compositing backward accumulated raw moments of s = G*dL/dG (see render_backward_kernel):
-        //   dL_dmeans2D[i] = (sum s*dx, sum s*dy), dL_dconic_op[i] = (sum s*dx^2, sum s*dx*dy, sum s*dy^2, sum s).
+        // The compositing backward accumulated raw moments of s = G*dL/dG:
+        //   (sum s*dx, sum s*dy) and (sum s*dx^2, sum s*dx*dy, sum s*dy^2, sum s).
         // With conic (cx,cy,cz) and opacity o:  dG/ddelx = -G (cx dx + cy dy), dG/dcx = -G dx^2 / 2, ...
-        const float4 mom = dL_dconic_op[i];
+        const float4 mom = make_float4(acc0.z, acc0.w, acc1.x, acc1.y);
         const float4 co = conic_opacity[i];
-        const float m1x = dL_dmeans2D[3 * i], m1y = dL_dmeans2D[3 * i + 1];
+        const float m1x = acc0.x, m1y = acc0.y;
         const float4 gco = make_float4(-0.5f * mom.x, -0.5f * mom.y, -0.5f * mom.z, 0.f);
         dop = co.w != 0.f ? mom.w / co.w : 0.f;
         const float gm0_ = -(co.x * m1x + co.y * m1y) * (0.5f * (float)cam.W);
@@ -556,8 +375,13 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
             dq[3] = 2.f * (-2.f * qz * dR[0][0] - qr * dR[0][1] + qx * dR[0][2] + qr * dR[1][0] - 2.f * qz * dR[1][1] + qy * dR[1][2] + qx * dR[2][0] + qy * dR[2][1]);
         }
     }
-    dL_dmeans2D_out[3 * i] = dm2[0];      // final d/dmeans2D (NDC-scaled, as upstream) replaces the moment scratch
-    dL_dmeans2D_out[3 * i + 1] = dm2[1];
+    dL_dmeans2D_out[3 * (size_t)i] = dm2[0];      // d/dmeans2D (NDC-scaled, as upstream); z stays 0
+    dL_dmeans2D_out[3 * (size_t)i + 1] = dm2[1];
+    dL_dmeans2D_out[3 * (size_t)i + 2] = 0.f;
+    if (dL_dcolors_out) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dL_dcolors_out[3 * (size_t)i + k] = dcol[k];
+    }
     if (src.S2 == 0) {
         out.dopacity[i] = dop;
 #pragma unroll
@@ -582,7 +406,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
         for (int k = 0; k < 3; ++k) {
             out.dxyz[v][3 * px + k] = dm[k];
             out.dscale[v][k * S2 + px] = dsc[k];
-            out.dimg[v][k * S2 + px] = 0.5f * dL_dcolors[3 * (size_t)i + k];    // colours were img*0.5+0.5
+            out.dimg[v][k * S2 + px] = 0.5f * dcol[k];    // colours were img*0.5+0.5
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) out.drot[v][k * S2 + px] = dq[k];
@@ -590,11 +414,11 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
 }
 
 int launch_preprocess_backward(const Camera& cam, int P, const GaussianSrc& src, const int32_t* radii,
-                               const float4* conic_opacity, float* dL_dmeans2D, const float4* dL_dconic_op,
-                               const float* dL_dcolors, const GaussianGrads& out, cudaStream_t stream) {
+                               const float4* conic_opacity, const float4* grad_acc, float* dL_dmeans2D, float* dL_dcolors,
+                               const GaussianGrads& out, cudaStream_t stream) {
     if (P <= 0) return GPSG_OK;
-    preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(cam, P, src, radii, conic_opacity, dL_dmeans2D,
-                                                                   dL_dmeans2D, dL_dconic_op, dL_dcolors, out);
+    preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(cam, P, src, radii, conic_opacity, grad_acc, dL_dmeans2D,
+                                                                   dL_dcolors, out);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
 }

@@ -29,7 +29,8 @@ __global__ void __launch_bounds__((kFwdWarps + 1) * 32, 8) render_forward_kernel
                                                                             const float4* __restrict__ slabA,
                                                                             const float4* __restrict__ slabB,
                                                                             const float4* __restrict__ slabC,
-                                                                            const uint2* __restrict__ ranges, const uint32_t* __restrict__ status,
+                                                                            const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
+                                                                            const uint32_t* __restrict__ status,
                                                                             float* __restrict__ final_T,
                                                                             uint32_t* __restrict__ n_contrib,
                                                                             float* __restrict__ out_color) {
@@ -41,8 +42,9 @@ __global__ void __launch_bounds__((kFwdWarps + 1) * 32, 8) render_forward_kernel
     __shared__ float4 qc[kFwdWarps][33];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile_y = blockIdx.y >> 1, half = blockIdx.y & 1;   // two CTAs per 16x16 tile
-    const int tile = tile_y * cam.grid_x + blockIdx.x;
+    // two CTAs per 16x16 tile; tiles are taken longest list first (tile_order, see tile_scan.cuh)
+    const int tile = (int)tile_order[blockIdx.x >> 1], half = blockIdx.x & 1;
+    const int tile_y = tile / cam.grid_x, tile_x = tile - tile_y * cam.grid_x;
     const uint2 range = status[2] ? make_uint2(0u, 0u) : ranges[tile];   // planned-mode overflow: render nothing
     const int total = (int)(range.y - range.x);
     const int nbatch = (total + kFwdChunk - 1) / kFwdChunk;
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__((kFwdWarps + 1) * 32, 8) render_forward_kernel
         return;
     }
     // ---------------- consumer warps: warp w covers the 8x4 block at ((w&1)*8, half*8 + (w>>1)*4) ----------------
-    const int bx0 = blockIdx.x * GPSG_TILE_X + ((warp & 1) << 3);
+    const int bx0 = tile_x * GPSG_TILE_X + ((warp & 1) << 3);
     const int by0 = tile_y * GPSG_TILE_Y + (half << 3) + ((warp >> 1) << 2);
     const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
     const bool inside = px < cam.W && py < cam.H;
@@ -162,8 +164,8 @@ __global__ void __launch_bounds__((kFwdWarps + 1) * 32, 8) render_forward_kernel
 }
 
 int launch_render_forward(const Camera& cam, BinningState b, ImageState im, float* out_color, cudaStream_t stream) {
-    dim3 grid(cam.grid_x, cam.grid_y * 2);
-    render_forward_kernel<<<grid, (kFwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges, im.totals,
+    const unsigned grid = 2u * (unsigned)(cam.grid_x * cam.grid_y);
+    render_forward_kernel<<<grid, (kFwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges, im.tile_order, im.totals,
                                                                     im.final_T, im.n_contrib, out_color);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;

@@ -9,13 +9,22 @@ namespace gpsg {
 // totals[0] = N, [1] = longest tile list, [2] = overflow flag (planned mode), [3] = number of big tiles (> kBigTile)
 constexpr uint32_t kBigTile = 2048;
 
+// Also emits `tile_order`: all tile ids, longest list first (64 buckets of 32 pairs; order inside a bucket is arbitrary).
+// The compositing kernels take their tile from this list, so the long tiles start first and the short / empty ones fill
+// the tail of the grid (longest-processing-time-first: ~2.4 waves of very unequal half-tile CTAs otherwise leave the SMs
+// idle at the end -- ncu r1: issue slots busy 78 % of active cycles but 66 % of elapsed).
+__device__ __forceinline__ uint32_t order_bucket(uint32_t c) { return 63u - min(63u, (c + 31u) >> 5); }
+
 __device__ __forceinline__ void tile_scan_block(int tiles, const ImageState& im, uint32_t capacity) {
     __shared__ uint32_t ws[32];
     __shared__ uint32_t s_max;
+    __shared__ uint32_t s_hist[64];
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = (nthr + 31) >> 5;
     const int per = (tiles + nthr - 1) / nthr;
     const int t0 = tid * per, t1 = min(tiles, t0 + per);
     if (tid == 0) s_max = 0;
+    if (tid < 64) s_hist[tid] = 0u;
+    __syncthreads();
     uint32_t sum = 0, mx = 0;
     constexpr int kReg = 16;                  // counts of up to 16 tiles per thread stay in registers (4096 tiles / 256 thr)
     uint32_t cnt[kReg];
@@ -34,12 +43,13 @@ __device__ __forceinline__ void tile_scan_block(int tiles, const ImageState& im,
         }
 #pragma unroll
         for (int k = 0; k < kReg; ++k)
-            if (k < per && t0 + k < tiles) { sum += cnt[k]; mx = max(mx, cnt[k]); }
+            if (k < per && t0 + k < tiles) { sum += cnt[k]; mx = max(mx, cnt[k]); atomicAdd(&s_hist[order_bucket(cnt[k])], 1u); }
     } else {
         for (int t = t0; t < t1; ++t) {
             const uint32_t c = __ldcg(&im.tile_count[t]);
             sum += c;
             mx = max(mx, c);
+            atomicAdd(&s_hist[order_bucket(c)], 1u);
         }
     }
     uint32_t v = sum;   // inclusive warp scan of the per-thread sums
@@ -61,11 +71,24 @@ __device__ __forceinline__ void tile_scan_block(int tiles, const ImageState& im,
     }
     mx = __reduce_max_sync(0xffffffffu, mx);
     if (lane == 0) atomicMax(&s_max, mx);
+    if (warp == 1 || nwarp == 1) {            // exclusive scan of the 64 length buckets -> first slot of each bucket
+        __syncwarp();
+        const uint32_t h0 = s_hist[2 * lane], h1 = s_hist[2 * lane + 1];
+        uint32_t w2 = h0 + h1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, w2, o);
+            if (lane >= o) w2 += u;
+        }
+        s_hist[2 * lane] = w2 - h0 - h1;
+        s_hist[2 * lane + 1] = w2 - h1;
+    }
     __syncthreads();
     uint32_t run = v - sum + (warp ? ws[warp - 1] : 0u);   // exclusive prefix of this thread's first tile
     auto emit = [&](int t, uint32_t c) {
         im.ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);   // empty tiles stay (0,0) as upstream
         im.tile_cursor[t] = 0u;
+        im.tile_order[atomicAdd(&s_hist[order_bucket(c)], 1u)] = (uint32_t)t;
         if (c > kBigTile) im.big_tiles[atomicAdd(&im.totals[3], 1u)] = (uint32_t)t;
         run += c;
     };

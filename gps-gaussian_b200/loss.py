@@ -53,14 +53,18 @@ class _L1SSIM(torch.autograd.Function):
                 _lib.check(rc, "gpsg_l1_ssim_forward")
         ctx.save_for_backward(x, y, *[m for m in maps if m is not None])
         ctx.cfg = (planes, H, W, float(w_l1), float(w_ssim), need, img.dtype, gt.dtype)
-        return out
+        # (loss, l1, ssim): only the loss carries a gradient; l1 / ssim are reporting values -- marked non-differentiable so
+        # that building a loss from them raises instead of silently producing zero gradients
+        loss, l1, ss = out[0].clone(), out[1].clone(), out[2].clone()
+        ctx.mark_non_differentiable(l1, ss)
+        return loss, l1, ss
 
     @staticmethod
-    def backward(ctx, grad_out):
+    def backward(ctx, grad_out, _g_l1=None, _g_ssim=None):
         planes, H, W, w_l1, w_ssim, need, dt_img, dt_gt = ctx.cfg
         saved = list(ctx.saved_tensors)
         x, y, rest = saved[0], saved[1], saved[2:]
-        g = grad_out.detach().to(torch.float32).contiguous()            # only g[0] reaches the image (device read, no sync)
+        g = grad_out.detach().to(torch.float32).reshape(1).contiguous()  # d/d(loss), read on the device (no sync)
         res = [None, None]
         stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
         with torch.cuda.device(x.device):
@@ -77,9 +81,8 @@ class _L1SSIM(torch.autograd.Function):
 
 def fused_l1_ssim(img, gt, w_l1=0.8, w_ssim=0.2):
     """== w_l1 * l1_loss(img, gt) + w_ssim * (1 - ssim(img, gt))   (reference train_stage2.py:70-72, without flow_loss)."""
-    out = _L1SSIM.apply(img, gt, w_l1, w_ssim)
-    loss = out[0]
-    loss.l1, loss.ssim = out[1].detach(), out[2].detach()
+    loss, l1, ss = _L1SSIM.apply(img, gt, w_l1, w_ssim)
+    loss.l1, loss.ssim = l1, ss
     return loss
 
 

@@ -20,9 +20,10 @@ import torch
 
 from . import _lib
 from .novel_calib import calib_from_data
-from .planned import PlannedRasterizer
+from .planned import PlannedRasterizer, exact_forward
 
 _VIEWS = ('lmain', 'rmain')
+_MAX_TILE_SORT = 4096          # kMaxTileSort (csrc/gpsg_internal.cuh): longest tile list the in-CTA sort takes
 
 
 def _settings(cal, b, r, height, width, bg_color):
@@ -99,6 +100,20 @@ class NovelViewRenderer:
             rast.forward_maps(settings, m['valid'], m['xyz'], m['img'], m['rot'], m['scale'], m['opacity'], out=out,
                               status_host=status_host)
 
+    def _render_exact(self, settings, b, out):
+        """Exact entry point (one host sync, radix fallback for over-long tile lists) for one view of sample b."""
+        if self.mode == 'compact':
+            f = self.flat[b]
+            exact_forward(settings, f['xyz'], f['rgb'], f['opacity'], f['scale'], f['rot'], self.H, self.W, out=out)
+        else:
+            from .GaussianRender import _RasterizeMaps
+            m = self.maps[b]
+            args = []
+            for v in range(2):
+                args += [m['valid'][v], m['xyz'][v], m['img'][v], m['rot'][v], m['scale'][v], m['opacity'][v]]
+            with torch.no_grad():
+                out.copy_(_RasterizeMaps.apply(settings, *args))
+
     def render(self, ratios, out=None, check=True):
         ratios = [float(r) for r in ratios]
         cal = calib_from_data(self.data, self.opt, ratios, *self.keys)
@@ -119,18 +134,30 @@ class NovelViewRenderer:
         if not check:
             return out                                                  # fully asynchronous; caller checks last_status
         torch.cuda.current_stream(self.dev).synchronize()
-        redo = [jobs[k] for k in range(len(jobs)) if int(status[k, 2]) != 0]
-        for (b, r) in redo:                                             # capacity overflow: grow once and re-render
+        # status[k] = (num_rendered, longest tile list, overflow flag) of job k.  Two different overflows:
+        #  * more pairs than the binning buffer holds -> size the buffer from the reported count and render again;
+        #  * a tile list longer than the in-CTA sort (kMaxTileSort = 4096): no buffer size helps -- that view goes through
+        #    the exact entry point, whose global radix fallback handles any list length.
+        for k, (b, r) in enumerate(jobs):
+            n_pairs, max_tile, overflow = (int(v) for v in status[k, :3].tolist())
+            if not overflow:
+                continue
+            settings = _settings(cal, b, r, self.H, self.W, self.bg)
+            if max_tile > _MAX_TILE_SORT:
+                self._render_exact(settings, b, out[b, r])
+                continue
             rast = self.rast[0]
-            for _ in range(8):
-                rast.grow()
-                rast.status_host.zero_()
-                self._enqueue(rast, _settings(cal, b, r, self.H, self.W, self.bg), b, out[b, r])
-                torch.cuda.synchronize(self.dev)
-                if rast.ok():
-                    break
-            else:
-                raise _lib.GpsgError("novel view render: pair capacity still exceeded after growing 8 times")
+            rast.grow(needed_pairs=n_pairs)
+            rast.status_host.zero_()
+            self._enqueue(rast, settings, b, out[b, r])
+            torch.cuda.synchronize(self.dev)
+            if not rast.ok():
+                st = rast.status()
+                if st["max_tile"] > _MAX_TILE_SORT:
+                    self._render_exact(settings, b, out[b, r])
+                else:
+                    raise _lib.GpsgError(f"novel view render: {st['num_rendered']} pairs do not fit capacity {rast.capacity}")
+        torch.cuda.synchronize(self.dev)
         return out
 
 

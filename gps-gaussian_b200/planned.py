@@ -17,6 +17,30 @@ from . import _lib
 from .introspect import make_settings
 
 
+def exact_forward(settings, means3D, colors, opacity, scales, rots, height, width, out=None):
+    """One forward through the exact (one host sync, allocator callbacks) entry point `gpsg_rasterize_forward` -- the path
+    that handles ANY scene, incl. tile lists longer than the in-CTA sort (global radix fallback).  Used by the sync-free
+    front ends when a view cannot be rendered from caller-owned buffers.  Returns the [3,H,W] image."""
+    dev = means3D.device
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    P = int(means3D.shape[0])
+    color = out if out is not None else torch.empty((3, int(height), int(width)), dtype=torch.float32, device=dev)
+    radii = torch.empty((max(P, 1),), dtype=torch.int32, device=dev)
+    n = C.c_int32(0)
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    _lib.begin_alloc(dev)
+    try:
+        with torch.cuda.device(dev):
+            rc = _lib.lib.gpsg_rasterize_forward(
+                C.byref(settings), idx, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), P, 0, p(means3D), p(colors),
+                None, p(opacity), p(scales), p(rots), None, p(color), p(radii), _lib.ALLOC_CB, C.c_void_p(1), _lib.ALLOC_CB,
+                C.c_void_p(2), _lib.ALLOC_CB, C.c_void_p(3), C.byref(n))
+    finally:
+        _lib.end_alloc()
+    _lib.check(rc, "gpsg_rasterize_forward")
+    return color
+
+
 class PlannedRasterizer:
     def __init__(self, P, height, width, capacity_pairs, device="cuda"):
         self.dev = torch.device(device)
@@ -83,9 +107,12 @@ class PlannedRasterizer:
     def ok(self):
         return not self.status()["overflow"]
 
-    def grow(self, factor=1.5):
-        st = self.status()
-        self._alloc_binning(max(int(st["num_rendered"] * factor), int(self.capacity * factor)))
+    def grow(self, factor=1.5, needed_pairs=None):
+        """Re-allocate the binning buffer.  `needed_pairs`: the pair count a failed job reported (its status words may
+        live in a caller-provided slot rather than self.status_host): the new capacity is sized from it directly."""
+        need = int(needed_pairs) if needed_pairs is not None else self.status()["num_rendered"]
+        self._alloc_binning(max(int(need * 1.05) + 1024, int(self.capacity * factor)) if need > self.capacity
+                            else int(self.capacity * factor))
         self.graph = None
 
     # ---- CUDA graph ----

@@ -109,3 +109,29 @@ def test_cached_sweep_grows_capacity_on_overflow(mode):
     out = small.render([0.5, 0.25])
     assert int(small.last_status[0, 2]) == 1                                # the tiny capacity did overflow...
     assert torch.equal(out[:, 0], big[:, 0])                                # ...and the re-render is exact
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["compact", "maps"])
+def test_cached_sweep_routes_overlong_tile_lists_through_the_exact_entry_point(mode, monkeypatch):
+    """an overflow caused by a tile list longer than the in-CTA sort cannot be cured by a larger buffer; such a view
+    must go through the exact entry point (radix fallback) instead of growing 8 times and raising.  Forced here by lowering
+    the threshold the redo logic compares `status[k,1]` (longest tile list) against; the capacity is sized from `status[k,0]`
+    in ONE step otherwise."""
+    from gps_gaussian_b200 import novel_views
+    from gps_gaussian_b200.novel_views import NovelViewRenderer
+    res = 96
+    data = _pair_data(res, (6,))
+    opt = OPTS["plain"]
+    big = NovelViewRenderer(data, opt, [0, 0, 0]).render([0.5, 0.25])
+    small = NovelViewRenderer(data, opt, [0, 0, 0], streams=1, capacity_pairs=64, mode=mode)
+    out = small.render([0.5, 0.25])
+    n_pairs = int(small.last_status[0, 0])
+    assert n_pairs > 64 and small.rast[0].capacity < 3 * n_pairs             # one growth step, sized from the job's own count
+    assert torch.equal(out, big)
+    monkeypatch.setattr(novel_views, "_MAX_TILE_SORT", 8)                     # every overflowed job now counts as "tile too long"
+    tiny = NovelViewRenderer(data, opt, [0, 0, 0], streams=2, capacity_pairs=64, mode=mode)
+    cap0 = tiny.rast[0].capacity
+    out2 = tiny.render([0.5, 0.25])
+    assert tiny.rast[0].capacity == cap0                                      # no blind growth ...
+    assert torch.equal(out2, big)                                             # ... the exact entry point rendered them
