@@ -149,6 +149,7 @@ static uint32_t* pinned_slot() {
 
 
 // ---- profiling -------------------------------------------------------------------------------
+#include <mutex>
 #include <vector>
 namespace gpsg {
 struct ProfSlot { cudaEvent_t a, b; Stage stage; bool used; };
@@ -158,12 +159,16 @@ struct Profiler {
     size_t next = 0;
     int launches[ST_COUNT] = {0};
 };
-static thread_local Profiler g_prof;
+// Process-wide (not thread-local): PyTorch runs autograd backward nodes on its own thread, and the backward launches of a
+// training step must land in the same accumulators as the forward launches issued from the caller's thread.
+static Profiler g_prof;
+static std::mutex g_prof_mu;
 static const char* kStageNames[ST_COUNT] = {"preprocess", "scan", "duplicate", "sort", "gather_ranges", "tile_scan",
                                             "bucket_scatter", "tile_sort_gather", "render_forward",
                                             "render_backward", "preprocess_backward", "corr_forward", "corr_backward", "corr_build"};
 StageTimer::StageTimer(Stage s, cudaStream_t st, int launches) : stage(s), stream(st), slot(nullptr) {
     if (!g_prof.on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     if (g_prof.on == 2) { g_prof.launches[s] += launches; return; }
     if (g_prof.next == g_prof.slots.size()) {
         ProfSlot ps; ps.used = false;
@@ -178,6 +183,7 @@ StageTimer::StageTimer(Stage s, cudaStream_t st, int launches) : stage(s), strea
 }
 StageTimer::~StageTimer() {
     if (!slot) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     cudaEventRecord(g_prof.slots[(size_t)(uintptr_t)slot - 1].b, stream);
 }
 }  // namespace gpsg
@@ -655,6 +661,7 @@ int gpsg_profile_enable(int on) {
 const char* gpsg_profile_stage_name(int stage) { return (stage >= 0 && stage < ST_COUNT) ? kStageNames[stage] : ""; }
 int gpsg_profile_read(float* total_ms, int32_t* calls, int32_t* launches, int capacity) {
     GPSG_REQUIRE(total_ms && calls && launches && capacity >= ST_COUNT, "profile_read: capacity < stage count");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     for (int i = 0; i < ST_COUNT; ++i) { total_ms[i] = 0.f; calls[i] = 0; launches[i] = g_prof.launches[i]; g_prof.launches[i] = 0; }
     for (size_t k = 0; k < g_prof.next; ++k) {
         ProfSlot& p = g_prof.slots[k];

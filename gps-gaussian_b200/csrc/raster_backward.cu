@@ -4,11 +4,18 @@
 #include "gpsg_internal.cuh"
 #include "slab_ring.cuh"
 
+#include <cstdlib>
+
 
 namespace gpsg {
 
 constexpr int kBwdChunk = 64;   // Gaussians per ring stage
-constexpr int kBwdStages = 8;
+#ifndef GPSG_BWD_STAGES
+#define GPSG_BWD_STAGES 8       // ring depth / CTAs per SM of the default backward kernel (tuning: build.py passes -D overrides)
+#endif
+#ifndef GPSG_BWD_BLOCKS
+#define GPSG_BWD_BLOCKS 4
+#endif
 constexpr int kBwdWarps = 4;    // consumer warps per CTA: 16 x 8 pixels (half a tile)
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -208,14 +215,265 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32, MIN_BLOCKS) render_backw
     if (slot > 0) flush(slot);
 }
 
-int launch_render_backward(const Camera& cam, BinningState b, ImageState im, const float* dL_dpix, float4* grad_acc,
-                           cudaStream_t stream) {
+// ---------------------------------------------------------------------------------------------------------------------
+// Round-2 variant of the above (default): the survivors of every 32-entry group are first rank-compacted, DEEPEST FIRST,
+// into a per-warp queue (as the forward does front to back), so the replay loop walks fixed shared-memory addresses two
+// survivors per iteration: no find-first-set / mask update / index arithmetic per survivor, and the loads, the conic
+// polynomial and the ex2 of the second survivor are issued before the first one's dependent transmittance / colour chain
+// (the r1 loop had one survivor in flight and ran at 62 % of the issue rate with 32 % of the warp slots occupied).
+// Ring + park buffers + queues exceed the 48 KB static limit, so the kernel takes its shared memory dynamically.
+// ---------------------------------------------------------------------------------------------------------------------
+struct __align__(16) BwdQueue {
+    float4 X[34];      // (mean x, mean y, Gaussian id bits, list position bits)
+    float4 B[34];      // log2-domain conic + opacity
+    float4 C[34];      // (r, g, b, -)
+};
+template <int STAGES>
+struct __align__(128) BwdSmem {
+    SlabRing<kBwdChunk, STAGES> ring;
+    BwdWarpBuf wbuf[kBwdWarps];
+    BwdQueue q[kBwdWarps];
+};
+
+template <int STAGES, int MIN_BLOCKS>
+__global__ void __launch_bounds__((kBwdWarps + 1) * 32, MIN_BLOCKS) render_backward_q_kernel(const __grid_constant__ Camera cam,
+                                                                               const float4* __restrict__ slabA,
+                                                                               const float4* __restrict__ slabB,
+                                                                               const float4* __restrict__ slabC,
+                                                                               const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
+                                                                               const uint32_t* __restrict__ status,
+                                                                               const float* __restrict__ final_T,
+                                                                               const uint32_t* __restrict__ n_contrib,
+                                                                               const float* __restrict__ dL_dpix,
+                                                                               float4* __restrict__ grad_acc) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    BwdSmem<STAGES>& sm = *reinterpret_cast<BwdSmem<STAGES>*>(smem_raw);
+    SlabRing<kBwdChunk, STAGES>& ring = sm.ring;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = (int)tile_order[blockIdx.x >> 1], half = blockIdx.x & 1;      // longest tile lists first (tile_scan.cuh)
+    const int tile_y = tile / cam.grid_x, tile_x = tile - tile_y * cam.grid_x;
+    const uint2 range = status[2] ? make_uint2(0u, 0u) : ranges[tile];   // planned-mode overflow: render nothing
+    const int total = (int)(range.y - range.x);
+
+    const int bx0 = tile_x * GPSG_TILE_X + ((warp & 1) << 3);
+    const int by0 = tile_y * GPSG_TILE_Y + (half << 3) + ((warp >> 1) << 2);
+    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
+    const bool inside = warp < kBwdWarps && px < cam.W && py < cam.H;
+    const float pixfx = (float)px, pixfy = (float)py;
+    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
+    const size_t HW = (size_t)cam.W * cam.H;
+    const size_t pid = (size_t)py * cam.W + px;
+    const float T_final = inside ? final_T[pid] : 0.0f;
+    const int last_contributor = inside ? (int)n_contrib[pid] : 0;
+    const int wmax = __reduce_max_sync(0xffffffffu, last_contributor);
+
+    if (tid == 0) ring_init(ring, kBwdWarps);
+    if (warp < kBwdWarps) {      // zero the queue so that pad / stale slots hold finite, non-contributing data (opacity 0)
+        for (int e = lane; e < 34; e += 32) {
+            sm.q[warp].X[e] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fffffff));
+            sm.q[warp].B[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sm.q[warp].C[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    __syncthreads();
+    if (lane == 0 && wmax > 0) atomicMax(&ring.hi, wmax);
+    __syncthreads();
+    const int hi = min(total, *(volatile int*)&ring.hi);
+    const int nbatch = (hi + kBwdChunk - 1) / kBwdChunk;
+
+    if (warp == kBwdWarps) {  // ---------------- producer warp ----------------
+        if (lane == 0)
+            ring_produce(ring, nbatch, kBwdWarps, slabA, slabB, slabC,
+                         [&](int b) { const int end = hi - b * kBwdChunk; return (size_t)range.x + (size_t)(end - min(kBwdChunk, end)); },
+                         [&](int b) { return min(kBwdChunk, hi - b * kBwdChunk); });
+        return;
+    }
+
+    BwdWarpBuf& wb = sm.wbuf[warp];
+    BwdQueue& Q = sm.q[warp];
+    float T = T_final;
+    float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f, lastc0 = 0.f, lastc1 = 0.f, lastc2 = 0.f, last_alpha = 0.f;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    if (inside) { g0 = dL_dpix[pid]; g1 = dL_dpix[HW + pid]; g2 = dL_dpix[2 * HW + pid]; }
+    wb.gpix[lane] = make_float4(g0, g1, g2, 0.f);
+    __syncwarp();
+    const float bg_dot = (cam.bg[0] * g0 + cam.bg[1] * g1) + cam.bg[2] * g2;
+    const float nTf_bg = -T_final * bg_dot;
+
+    const int qj = lane & (kQ - 1), qh = lane >> 4;
+    const float fx0 = (float)bx0, fy0 = (float)(by0 + 2 * qh);
+    const unsigned gt_mask = lane == 31 ? 0u : (0xffffffffu << (lane + 1));   // lanes above this one
+    int slot = 0;
+
+    auto flush = [&](int cnt) {
+        __syncwarp();
+        const float4 me = wb.meta[qj];
+        const bool on = qj < cnt;
+        const float dxb = me.x - fx0, dy0 = me.y - fy0, dy1 = dy0 - 1.0f;
+        float m0 = 0.f, m1 = 0.f, k0 = 0.f, k1 = 0.f, k2 = 0.f, k3 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < 16; ++pp) {
+            const int p = qh * 16 + pp;
+            const float sv = wb.S[qj][p];
+            const float wv = wb.Wt[qj][p];
+            const float4 gp = wb.gpix[p];
+            const float dx = dxb - (float)(pp & 7);
+            const float dy = (pp & 8) ? dy1 : dy0;
+            const float sx = sv * dx, sy = sv * dy;
+            m0 += sx;
+            m1 += sy;
+            k0 = fmaf(sx, dx, k0);
+            k1 = fmaf(sx, dy, k1);
+            k2 = fmaf(sy, dy, k2);
+            k3 += sv;
+            c0 = fmaf(wv, gp.x, c0);
+            c1 = fmaf(wv, gp.y, c1);
+            c2 = fmaf(wv, gp.z, c2);
+        }
+        m0 += __shfl_xor_sync(0xffffffffu, m0, 16);
+        m1 += __shfl_xor_sync(0xffffffffu, m1, 16);
+        k0 += __shfl_xor_sync(0xffffffffu, k0, 16);
+        k1 += __shfl_xor_sync(0xffffffffu, k1, 16);
+        k2 += __shfl_xor_sync(0xffffffffu, k2, 16);
+        k3 += __shfl_xor_sync(0xffffffffu, k3, 16);
+        c0 += __shfl_xor_sync(0xffffffffu, c0, 16);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, 16);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, 16);
+        if (on) {
+            const uint32_t id = __float_as_uint(me.z);
+            float4* acc = grad_acc + 3 * (size_t)id;
+            if (qh == 0) {
+                if (m0 != 0.f || m1 != 0.f || k0 != 0.f || k1 != 0.f) atomicAdd(acc, make_float4(m0, m1, k0, k1));
+            } else {
+                if (k2 != 0.f || k3 != 0.f || c0 != 0.f || c1 != 0.f) atomicAdd(acc + 1, make_float4(k2, k3, c0, c1));
+                if (c2 != 0.f) atomicAdd(reinterpret_cast<float*>(acc + 2), c2);
+            }
+        }
+        __syncwarp();
+    };
+
+    // dependent part of one survivor (see the header of render_backward_gm_kernel for the branch-free state update)
+    auto chain = [&](const float4& xq, const float4& q, const float4& c, float G, bool active) {
+        const float Ge = active ? G : 0.0f;
+        const float alpha_e = fminf(0.99f, q.w * Ge);
+        float inv1ma;                                 // 1 - alpha >= 0.01: MUFU.RCP (1 ulp) without the slow path
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1ma) : "f"(1.0f - alpha_e));
+        T *= inv1ma;
+        accum0 = fmaf(last_alpha, lastc0 - accum0, accum0);
+        accum1 = fmaf(last_alpha, lastc1 - accum1, accum1);
+        accum2 = fmaf(last_alpha, lastc2 - accum2, accum2);
+        float dL_dalpha = (c.x - accum0) * g0;
+        dL_dalpha = fmaf(c.y - accum1, g1, dL_dalpha);
+        dL_dalpha = fmaf(c.z - accum2, g2, dL_dalpha);
+        dL_dalpha = fmaf(dL_dalpha, T, nTf_bg * inv1ma);
+        wb.S[slot][lane] = Ge * (q.w * dL_dalpha);
+        wb.Wt[slot][lane] = alpha_e * T;
+        if (lane == 0) wb.meta[slot] = make_float4(xq.x, xq.y, xq.z, 0.f);
+        lastc0 = c.x; lastc1 = c.y; lastc2 = c.z;
+        last_alpha = alpha_e;
+        if (++slot == kQ) { flush(kQ); slot = 0; }
+    };
+
+    for (int b = 0; b < nbatch; ++b) {
+        ring_wait_full(ring, b, kBwdWarps + 1 /* never "all done" in the backward */);
+        const int s = b % STAGES;
+        const int end = hi - b * kBwdChunk;
+        const int n = min(kBwdChunk, end);
+        const int start = end - n;
+        if (start < wmax) {
+            const float4* __restrict__ SA = ring.A[s];
+            const float4* __restrict__ SB = ring.B[s];
+            const float4* __restrict__ SC = ring.C[s];
+            for (int base = ((n - 1) >> 5) << 5; base >= 0; base -= 32) {
+                if (start + base >= wmax) continue;
+                const int my = base + lane;
+                bool hit = false;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (my < n && start + my < wmax) {
+                    a = SA[my];
+                    hit = (a.x >= wx0 - a.z) && (a.x <= wx1 + a.z) && (a.y >= wy0 - a.w) && (a.y <= wy1 + a.w);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (!m) continue;
+                const int cnt = __popc(m);
+                if (hit) {                                   // back to front: rank = number of surviving lanes ABOVE this one
+                    const int r = __popc(m & gt_mask);
+                    const float4 c = SC[my];
+                    Q.X[r] = make_float4(a.x, a.y, c.w, __int_as_float(start + my));
+                    Q.B[r] = SB[my];
+                    Q.C[r] = c;
+                }
+                if (lane == 0) {                             // pad odd counts: position "infinity" -> never active
+                    Q.X[cnt] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fffffff));
+                    Q.B[cnt] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                __syncwarp();
+#pragma unroll 2
+                for (int i = 0; i < cnt; i += 2) {
+                    const float4 xa = Q.X[i], xb = Q.X[i + 1];
+                    const float4 qa = Q.B[i], qb = Q.B[i + 1];
+                    const float4 ca = Q.C[i], cb = Q.C[i + 1];
+                    const float dxa = xa.x - pixfx, dya = xa.y - pixfy, dxb2 = xb.x - pixfx, dyb = xb.y - pixfy;
+                    const float pa = fmaf(qa.z * dya, dya, fmaf(qa.x, dxa, qa.y * dya) * dxa);   // log2e * power
+                    const float pb = fmaf(qb.z * dyb, dyb, fmaf(qb.x, dxb2, qb.y * dyb) * dxb2);
+                    const float Ga = ex2_approx(pa), Gb = ex2_approx(pb);
+                    const bool acta = __float_as_int(xa.w) < last_contributor && !(pa > 0.0f) && !(fminf(0.99f, qa.w * Ga) < 1.0f / 255.0f);
+                    const bool actb = __float_as_int(xb.w) < last_contributor && !(pb > 0.0f) && !(fminf(0.99f, qb.w * Gb) < 1.0f / 255.0f);
+                    const unsigned va = __ballot_sync(0xffffffffu, acta), vb = __ballot_sync(0xffffffffu, actb);
+                    if (va) chain(xa, qa, ca, Ga, acta);
+                    if (vb) chain(xb, qb, cb, Gb, actb);
+                }
+                __syncwarp();                                // the queue is rewritten by the next group
+            }
+        }
+        ring_release(ring, b, lane);
+    }
+    if (slot > 0) flush(slot);
+}
+
+template <typename K>
+static int set_dyn_smem(K kernel, size_t bytes) {
+    static thread_local int done_dev = -1;
+    int dev = 0;
+    GPSG_CUDA(cudaGetDevice(&dev));
+    if (done_dev != dev) {
+        GPSG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        done_dev = dev;
+    }
+    return GPSG_OK;
+}
+
+template <int STAGES, int BLOCKS>
+static int launch_q(const Camera& cam, BinningState b, ImageState im, const float* dL_dpix, float4* grad_acc, cudaStream_t stream) {
     const unsigned grid = 2u * (unsigned)(cam.grid_x * cam.grid_y);
-    render_backward_gm_kernel<8, 5><<<grid, (kBwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges,
-                                                                              im.tile_order, im.totals, im.final_T, im.n_contrib, dL_dpix,
-                                                                              grad_acc);
+    auto kern = render_backward_q_kernel<STAGES, BLOCKS>;
+    const size_t smem = sizeof(BwdSmem<STAGES>);
+    int rc = set_dyn_smem(kern, smem);
+    if (rc) return rc;
+    kern<<<grid, (kBwdWarps + 1) * 32, smem, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges, im.tile_order, im.totals,
+                                                      im.final_T, im.n_contrib, dL_dpix, grad_acc);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
+}
+
+int launch_render_backward(const Camera& cam, BinningState b, ImageState im, const float* dL_dpix, float4* grad_acc,
+                           cudaStream_t stream) {
+    static const int variant = [] { const char* e = getenv("GPSG_BWD_VARIANT"); return e ? atoi(e) : 0; }();   // TUNING ONLY
+    switch (variant) {
+        case 1: return launch_q<6, 4>(cam, b, im, dL_dpix, grad_acc, stream);
+        case 2: return launch_q<6, 5>(cam, b, im, dL_dpix, grad_acc, stream);
+        case 3: return launch_q<10, 4>(cam, b, im, dL_dpix, grad_acc, stream);
+        case 4: {
+            const unsigned grid = 2u * (unsigned)(cam.grid_x * cam.grid_y);
+            render_backward_gm_kernel<8, 5><<<grid, (kBwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges,
+                                                                                      im.tile_order, im.totals, im.final_T,
+                                                                                      im.n_contrib, dL_dpix, grad_acc);
+            GPSG_LAUNCH_CHECK();
+            return GPSG_OK;
+        }
+        default: return launch_q<8, 4>(cam, b, im, dL_dpix, grad_acc, stream);
+    }
 }
 
 // A.7 + A.8 fused: per Gaussian, (dL/dmean2D, dL/dconic) -> dL/d{mean3D, cov3D, scale, rotation}.

@@ -30,6 +30,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Same, but the hardware may keep the thread suspended for up to `ns` nanoseconds while the phase is incomplete (it is woken
+// as soon as the phase completes).  A software poll loop (try_wait + nanosleep + flag check + branch, ~7 instructions per
+// iteration) in the slab producers cost 20 % (forward) / 26 % (backward) of ALL executed warp instructions of the two
+// issue-bound compositing kernels (ncu r2, profiles/r2_prof_*_summary.md); with the hint an iteration is rare.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }

@@ -226,7 +226,7 @@ GPSG_API int gpsg_l1_ssim_backward(int device, void* stream, int planes, int H, 
  * When enabled, every stage of the forward/backward is bracketed by CUDA events on the launching stream.
  * gpsg_profile_read() synchronises, then returns for stage i: total_ms[i] (summed over the calls since the last
  * reset), calls[i] and the number of kernel launches[i]; it returns the number of stages (names via
- * gpsg_profile_stage_name) and resets the accumulators.  Thread-local.  on = 2 counts launches only (no events: nothing is
+ * gpsg_profile_stage_name) and resets the accumulators.  Process-wide (autograd runs backward nodes on its own thread).  on = 2 counts launches only (no events: nothing is
  * inserted into the streams, for timed regions that should only be counted). */
 GPSG_API int gpsg_profile_enable(int on);
 GPSG_API int gpsg_profile_read(float* total_ms, int32_t* calls, int32_t* launches, int capacity);
