@@ -226,10 +226,12 @@ static int forward_exact(const GpsgRasterSettings* s, int device, cudaStream_t s
     if (P > 0) {
         uint32_t* slot = pinned_slot();
         GPSG_REQUIRE(slot != nullptr, "cudaHostAlloc failed");
-        GPSG_CUDA(cudaMemcpyAsync(slot, im.totals, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        GPSG_CUDA(cudaMemcpyAsync(slot, im.totals, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         GPSG_CUDA(cudaStreamSynchronize(stream));
         N = slot[0];
         max_count = slot[1];
+        GPSG_REQUIRE(slot[5] == 0u, "more than 2^31 (tile, Gaussian) pairs: the splats cover (almost) the whole image each -- "
+                                    "degenerate scene (32-bit pair offsets, as in the upstream rasterizer)");
     }
     if (num_rendered) *num_rendered = (int32_t)N;
     if (shs && P > 0) {   // SH -> RGB for the visible Gaussians (kept in the geometry buffer for the backward)

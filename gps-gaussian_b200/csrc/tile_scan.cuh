@@ -6,7 +6,8 @@
 
 namespace gpsg {
 
-// totals[0] = N, [1] = longest tile list, [2] = overflow flag (planned mode), [3] = number of big tiles (> kBigTile)
+// totals[0] = N, [1] = longest tile list, [2] = overflow flag (planned mode), [3] = number of big tiles (> kBigTile),
+// [4] = preprocess CTA ticket, [5] = 1 if the scene has more than 2^31 (tile, Gaussian) pairs (refused)
 constexpr uint32_t kBigTile = 2048;
 
 // Also emits `tile_order`: all tile ids, longest list first (64 buckets of 32 pairs; order inside a bucket is arbitrary).
@@ -19,10 +20,11 @@ __device__ __forceinline__ void tile_scan_block(int tiles, const ImageState& im,
     __shared__ uint32_t ws[32];
     __shared__ uint32_t s_max;
     __shared__ uint32_t s_hist[64];
+    __shared__ unsigned long long s_total64;
     const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = (nthr + 31) >> 5;
     const int per = (tiles + nthr - 1) / nthr;
     const int t0 = tid * per, t1 = min(tiles, t0 + per);
-    if (tid == 0) s_max = 0;
+    if (tid == 0) { s_max = 0; s_total64 = 0ull; }
     if (tid < 64) s_hist[tid] = 0u;
     __syncthreads();
     uint32_t sum = 0, mx = 0;
@@ -51,6 +53,12 @@ __device__ __forceinline__ void tile_scan_block(int tiles, const ImageState& im,
             mx = max(mx, c);
             atomicAdd(&s_hist[order_bucket(c)], 1u);
         }
+    }
+    {   // 64-bit total: the 32-bit prefix sums below wrap beyond 2^32 pairs (every splat covering the whole image)
+        unsigned long long s64 = (unsigned long long)sum;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s64 += __shfl_xor_sync(0xffffffffu, s64, o);
+        if (lane == 0) atomicAdd(&s_total64, s64);
     }
     uint32_t v = sum;   // inclusive warp scan of the per-thread sums
 #pragma unroll
@@ -101,10 +109,12 @@ __device__ __forceinline__ void tile_scan_block(int tiles, const ImageState& im,
     }
     if (tid == nthr - 1) {
         const uint32_t total = ws[nwarp - 1];
-        im.totals[0] = total;
+        const bool too_many = s_total64 > 0x7fffffffull;     // pair offsets are 32-bit (as upstream's): refuse, do not wrap
+        im.totals[0] = too_many ? 0u : total;
         im.totals[1] = s_max;
         // planned (sync-free) mode: later kernels skip their work if the pairs do not fit / a tile is too long
-        im.totals[2] = (capacity != 0u && (total > capacity || s_max > kMaxTileSort)) ? 1u : 0u;
+        im.totals[2] = ((capacity != 0u && (total > capacity || s_max > kMaxTileSort)) || too_many) ? 1u : 0u;
+        im.totals[5] = too_many ? 1u : 0u;
     }
 }
 

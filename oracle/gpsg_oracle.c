@@ -162,6 +162,7 @@ int SUFFIX(oracle_preprocess)(int P, int W, int H, const real* means3D, const re
         real disc = R_SQRT(rmax(RC(0.1), mid * mid - det));
         real lambda1 = mid + disc, lambda2 = mid - disc;
         int my_radius = f2i_sat(R_CEIL(RC(3.0) * R_SQRT(rmax(lambda1, lambda2))));
+        if (my_radius <= 0) continue; /* only a NaN covariance gets here (finite: >= 2): culled, see raster_preprocess.cu */
         real px = ((ndcx + RC(1.0)) * (real)W - RC(1.0)) * RC(0.5);
         real py = ((ndcy + RC(1.0)) * (real)H - RC(1.0)) * RC(0.5);
         int r[4];

@@ -66,7 +66,10 @@ def project(means3D, scales, rots, opacity, view, proj, tanfovx, tanfovy, W, H, 
     conic = np.stack([c / det_s, -b / det_s, a / det_s], 1)
     mid = 0.5 * (a + c)
     lam = mid + np.sqrt(np.maximum(f8(np.float32(0.1)), mid * mid - det))
-    radius = np.ceil(3.0 * np.sqrt(lam)).astype(np.int64)
+    with np.errstate(invalid="ignore"):
+        rad_f = np.ceil(3.0 * np.sqrt(lam))
+    ok &= np.isfinite(rad_f) & (rad_f > 0)                         # NaN covariance -> culled (finite inputs: radius >= 2)
+    radius = np.where(ok, rad_f, 0).astype(np.int64)
     pix = np.stack([((ndc[:, 0] + 1.0) * W - 1.0) * 0.5, ((ndc[:, 1] + 1.0) * H - 1.0) * 0.5], 1)
     gx, gy = (W + TILE - 1) // TILE, (H + TILE - 1) // TILE
     rad = radius.astype(f8)

@@ -137,6 +137,23 @@ def test_independent_numpy_restatement_agrees_with_the_c_oracle(P, res, kw):
     assert np.array_equal(a["n_contrib"], b["n_contrib"])
 
 
+def test_non_finite_inputs_are_culled_in_both_restatements():
+    """NaN / inf scales, rotations, positions: culled (radius 0 is not a splat), so sum(tiles_touched) == number of emitted
+    pairs -- the invariant whose violation crashed the tile sort on the device (tests/test_raster_gpu.py has the GPU half)."""
+    from oracle import raster_independent as ri
+    sc = synth.random_cube_scene(3000, 128, seed=3)
+    sc["scales"][::7] = np.nan; sc["rots"][3::11] = np.nan; sc["means3D"][1::13] = np.nan
+    sc["means3D"][5::17, 0] = np.inf; sc["scales"][2::23, 1] = np.inf
+    for dt in ("f32", "f64"):
+        _, a = oracle_forward(sc, dt)
+        assert a["num_rendered"] == int(a["tiles_touched"].sum()) == int((a["ranges"][:, 1].astype(np.int64) - a["ranges"][:, 0]).sum())
+        assert np.all((a["radii"] > 0) == (a["tiles_touched"] > 0)) and np.isfinite(a["color"]).all()
+    with np.errstate(all="ignore"):
+        b = ri.forward_scene(sc)
+    assert np.array_equal(a["radii"], b["radii"]) and np.array_equal(a["vals"], b["point_list"])
+    assert np.abs(a["color"] - b["color"]).max() < 1e-12
+
+
 def test_binning_invariants():
     sc = synth.random_cube_scene(5000, 200, seed=5)               # 200 is not a multiple of 16
     _, st = oracle_forward(sc, "f32")

@@ -22,6 +22,7 @@ pytestmark = pytest.mark.gpu
 def _run(sc):
     from gps_gaussian_b200.introspect import RasterCall
     rc = RasterCall(sc)
+    rc.color.fill_(float("nan"))          # poison: a tile the kernels never visit cannot pass on stale allocator contents
     rc.forward()
     torch.cuda.synchronize()
     return rc
@@ -124,6 +125,42 @@ def test_device_against_the_independent_numpy_restatement(P, res, kw):
     assert ok.mean() > 0.95
     assert d[ok].max() <= RGB_TOL, d[ok].max()
     assert np.array_equal(_np(st["n_contrib"]).view(np.uint32).reshape(sc["H"], sc["W"])[ok], ind["n_contrib"][ok])
+
+
+def _poison(sc, seed=0):
+    """NaN / inf in the per-Gaussian inputs, as an fp16 overflow inside the AMP network produces them (observed at step 18 of
+    the C5-size stage-2 run: every scale / rotation / opacity NaN, half of the positions NaN)."""
+    sc = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in sc.items()}
+    sc["scales"][::7] = np.nan
+    sc["rots"][3::11] = np.nan
+    sc["means3D"][1::13] = np.nan
+    sc["means3D"][5::17, 0] = np.inf
+    sc["means3D"][6::19] = -np.inf
+    sc["scales"][2::23, 1] = np.inf
+    return sc
+
+
+def test_non_finite_inputs_are_culled_not_crashed():
+    """A NaN covariance converts to radius 0, whose 1-tile rectangle used to be COUNTED into the tile (tiles_touched = 1)
+    but skipped by the scatter (radii <= 0): the tile list kept an uninitialised pair -> illegal address in the tile sort
+    (found by running the reference's stage-2 loop at C5 size for 18 steps).  Such splats are now culled -- here, in the
+    oracle and in the independent restatement alike; everything else about the scene stays bit-exact."""
+    sc = _poison(synth.random_cube_scene(8000, 200, spread=0.6, scale_mul=2.0, seed=31, bg=(0.2, 0.3, 0.4)))
+    rc, ref = _assert_forward_parity(sc, tag="nonfinite")
+    bad = ~(np.isfinite(sc["scales"]).all(1) & np.isfinite(sc["rots"]).all(1) & np.isfinite(sc["means3D"]).all(1))
+    assert bad.sum() > 1000 and int((_np(rc.radii)[bad] != 0).sum()) == 0 and int((_np(rc.radii)[~bad] > 0).sum()) > 3000
+    assert bool(torch.isfinite(rc.color).all())
+    got = rc.backward(torch.randn(3, 200, 200, device="cuda", generator=torch.Generator("cuda").manual_seed(1)))
+    for k in ("dL_dmeans3D", "dL_dscales", "dL_drots", "dL_dopacity", "dL_dcolors"):
+        g = _np(got[k]).reshape(8000, -1)
+        assert np.isfinite(g).all() and float(np.abs(g[bad]).sum()) == 0.0, k          # culled: exactly zero gradient
+    # the all-NaN frame of the real failure: nothing visible, background only, backward is a no-op
+    allnan = dict(sc)
+    allnan["scales"] = np.full_like(sc["scales"], np.nan); allnan["rots"] = np.full_like(sc["rots"], np.nan)
+    allnan["opacity"] = np.full_like(sc["opacity"], np.nan)
+    rc2 = _run(allnan)
+    assert rc2.num_rendered == 0 and int(rc2.radii.abs().sum()) == 0
+    assert torch.allclose(rc2.color, torch.tensor(sc["bg"], device="cuda")[:, None, None].expand(3, 200, 200))
 
 
 def test_cov3d_precomp_path_matches_scale_rot_path():
