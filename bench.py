@@ -116,12 +116,13 @@ def bench_config(V, R, **extra):
     return cfg
 
 
-def _source_hash():
-    """sha256 over the compositing kernels' sources: stamps profiles/render_forward_traffic.json so a stale ncu traffic
+def _source_hash(kernel="render_forward_kernel"):
+    """sha256 over the sources of a compositing kernel: stamps profiles/render_forward_traffic.json so a stale ncu traffic
     figure is refused instead of silently reported (VERDICT r1 weak #12)."""
     import hashlib
     h = hashlib.sha256()
-    for f in ("raster_render.cu", "slab_ring.cuh", "gpsg_internal.cuh"):
+    main = "raster_backward.cu" if "backward" in kernel else "raster_render.cu"
+    for f in (main, "slab_ring.cuh", "tma_bulk.cuh", "gpsg_internal.cuh"):
         with open(os.path.join(ROOT, "gps-gaussian_b200", "csrc", f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()
@@ -136,7 +137,7 @@ def _traffic(kernel):
     ent = j.get(kernel) if isinstance(j.get(kernel), dict) else (j if kernel == "render_forward_kernel" else None)
     if not ent:
         return None, "kernel not in traffic file"
-    if ent.get("source_sha256") != _source_hash():
+    if ent.get("source_sha256") != _source_hash(kernel):
         return None, "stale: kernel sources changed since the ncu capture (source_sha256 mismatch)"
     return float(ent["dram_bytes_per_launch"]), ent.get("from", "ncu --set full")
 
@@ -547,6 +548,9 @@ def run_c5(args, rank, world, local_rank):
         harness.c3_step(st, dict_copy(batches[k % 2]), pts2render=ref_gr.pts2render, allreduce=ar)
     sampler = ClockSampler(local_rank)
     res_ms = {}
+    from gps_gaussian_b200 import _lib
+    _lib.profile_enable(2)                     # count our own kernel launches (process-wide: the backward runs on autograd's thread)
+    _lib.profile_read()
     for label, fn in (("with_allreduce", ar), ("without_allreduce", None)):
         shard.barrier(dev)
         if label == "with_allreduce":
@@ -562,6 +566,7 @@ def run_c5(args, rank, world, local_rank):
         res_ms[label + "_stages"] = {k: v / args.steps for k, v in timers.items()}
         if label == "with_allreduce":
             clocks = sampler.stop()
+            launches = sum(v["launches"] for v in _lib.profile_read().values())
     # replicas must still be identical after the averaged updates
     flat = torch.cat([p.detach().reshape(-1) for p in st.model.parameters()])
     chk = torch.stack([flat.double().sum(), flat.double().abs().sum()])
@@ -578,9 +583,14 @@ def run_c5(args, rank, world, local_rank):
                 "config": {"workload": f"C5: stage-2 training, reference RtStereoHumanModel from baseline/_ref, 2 pairs/GPU of {res}^2 "
                                        f"(render {2 * res}^2), global batch {2 * world}, flat NCCL all-reduce of 5144408 fp32 grads",
                            "fast_paths": "GPSG_PATCH fused paths" if args.patch else "plain drop-ins", "parallelism": f"dp{world}"},
-                "exposed_comm_ms": ms - res_ms["without_allreduce"], "ms_per_step_without_allreduce": res_ms["without_allreduce"],
+                "exposed_comm_ms": res_ms["with_allreduce_stages"].get("allreduce"),
+                "exposed_comm_note": "CUDA-event time of the all-reduce stage between backward and unscale_ (flatten + NCCL SUM + "
+                                     "divide + unflatten; nothing overlaps it); the step-time difference of two separate loops is also given "
+                                     "but includes the drift of the training state",
+                "step_ms_minus_step_ms_without_allreduce": ms - res_ms["without_allreduce"],
+                "ms_per_step_without_allreduce": res_ms["without_allreduce"],
                 "stages_ms": res_ms["with_allreduce_stages"], "allreduce_bytes": 5144408 * 4, "replicas_in_sync": in_sync,
-                "clocks": clocks, "gpu_launches": None}
+                "clocks": clocks, "gpu_launches": int(launches)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

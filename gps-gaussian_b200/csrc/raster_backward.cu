@@ -4,8 +4,6 @@
 #include "gpsg_internal.cuh"
 #include "slab_ring.cuh"
 
-#include <cstdlib>
-
 
 namespace gpsg {
 
@@ -46,182 +44,13 @@ struct __align__(16) BwdWarpBuf {
     float Wt[kQ][33];
 };
 
-// STAGES x 64-entry ring, MIN_BLOCKS CTAs / SM.  Measured on C2: <8,5> 303 us, <6,5> 327, <5,6> 333, <4,6> 353 -- the
-// producer lane needs the deeper ring more than the SM needs a sixth CTA (44.8 KB of static shared memory / CTA: 5 fit).
-template <int STAGES, int MIN_BLOCKS>
-__global__ void __launch_bounds__((kBwdWarps + 1) * 32, MIN_BLOCKS) render_backward_gm_kernel(const __grid_constant__ Camera cam,
-                                                                                const float4* __restrict__ slabA,
-                                                                                const float4* __restrict__ slabB,
-                                                                                const float4* __restrict__ slabC,
-                                                                                const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order,
-                                                                                const uint32_t* __restrict__ status,
-                                                                                const float* __restrict__ final_T,
-                                                                                const uint32_t* __restrict__ n_contrib,
-                                                                                const float* __restrict__ dL_dpix,
-                                                                                float4* __restrict__ grad_acc) {
-    __shared__ SlabRing<kBwdChunk, STAGES> ring;
-    __shared__ BwdWarpBuf wbuf[kBwdWarps];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = (int)tile_order[blockIdx.x >> 1], half = blockIdx.x & 1;      // longest tile lists first (tile_scan.cuh)
-    const int tile_y = tile / cam.grid_x, tile_x = tile - tile_y * cam.grid_x;
-    const uint2 range = status[2] ? make_uint2(0u, 0u) : ranges[tile];   // planned-mode overflow: render nothing
-    const int total = (int)(range.y - range.x);
-
-    const int bx0 = tile_x * GPSG_TILE_X + ((warp & 1) << 3);
-    const int by0 = tile_y * GPSG_TILE_Y + (half << 3) + ((warp >> 1) << 2);
-    const int px = bx0 + (lane & 7), py = by0 + (lane >> 3);
-    const bool inside = warp < kBwdWarps && px < cam.W && py < cam.H;
-    const float pixfx = (float)px, pixfy = (float)py;
-    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
-    const size_t HW = (size_t)cam.W * cam.H;
-    const size_t pid = (size_t)py * cam.W + px;
-    const float T_final = inside ? final_T[pid] : 0.0f;
-    const int last_contributor = inside ? (int)n_contrib[pid] : 0;
-    const int wmax = __reduce_max_sync(0xffffffffu, last_contributor);
-
-    if (tid == 0) ring_init(ring, kBwdWarps);
-    __syncthreads();
-    if (lane == 0 && wmax > 0) atomicMax(&ring.hi, wmax);
-    __syncthreads();
-    const int hi = min(total, *(volatile int*)&ring.hi);
-    const int nbatch = (hi + kBwdChunk - 1) / kBwdChunk;
-
-    if (warp == kBwdWarps) {  // ---------------- producer warp ----------------
-        if (lane == 0)
-            ring_produce(ring, nbatch, kBwdWarps, slabA, slabB, slabC,
-                         [&](int b) { const int end = hi - b * kBwdChunk; return (size_t)range.x + (size_t)(end - min(kBwdChunk, end)); },
-                         [&](int b) { return min(kBwdChunk, hi - b * kBwdChunk); });
-        return;
-    }
-
-    BwdWarpBuf& wb = wbuf[warp];
-    float T = T_final;
-    float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f, lastc0 = 0.f, lastc1 = 0.f, lastc2 = 0.f, last_alpha = 0.f;
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-    if (inside) { g0 = dL_dpix[pid]; g1 = dL_dpix[HW + pid]; g2 = dL_dpix[2 * HW + pid]; }
-    wb.gpix[lane] = make_float4(g0, g1, g2, 0.f);
-    __syncwarp();
-    const float bg_dot = (cam.bg[0] * g0 + cam.bg[1] * g1) + cam.bg[2] * g2;
-
-    // Gaussian-major role of this lane: Gaussian slot qj, pixel rows 2*qh and 2*qh+1 of the block
-    const int qj = lane & (kQ - 1), qh = lane >> 4;
-    const float fx0 = (float)bx0, fy0 = (float)(by0 + 2 * qh);
-    int slot = 0;
-
-    auto flush = [&](int cnt) {
-        __syncwarp();
-        const float4 me = wb.meta[qj];
-        const bool on = qj < cnt;
-        const float dxb = me.x - fx0, dy0 = me.y - fy0, dy1 = dy0 - 1.0f;
-        float m0 = 0.f, m1 = 0.f, k0 = 0.f, k1 = 0.f, k2 = 0.f, k3 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-#pragma unroll
-        for (int pp = 0; pp < 16; ++pp) {
-            const int p = qh * 16 + pp;
-            const float sv = wb.S[qj][p];
-            const float wv = wb.Wt[qj][p];
-            const float4 gp = wb.gpix[p];
-            const float dx = dxb - (float)(pp & 7);
-            const float dy = (pp & 8) ? dy1 : dy0;
-            const float sx = sv * dx, sy = sv * dy;
-            m0 += sx;
-            m1 += sy;
-            k0 = fmaf(sx, dx, k0);
-            k1 = fmaf(sx, dy, k1);
-            k2 = fmaf(sy, dy, k2);
-            k3 += sv;
-            c0 = fmaf(wv, gp.x, c0);
-            c1 = fmaf(wv, gp.y, c1);
-            c2 = fmaf(wv, gp.z, c2);
-        }
-        m0 += __shfl_xor_sync(0xffffffffu, m0, 16);
-        m1 += __shfl_xor_sync(0xffffffffu, m1, 16);
-        k0 += __shfl_xor_sync(0xffffffffu, k0, 16);
-        k1 += __shfl_xor_sync(0xffffffffu, k1, 16);
-        k2 += __shfl_xor_sync(0xffffffffu, k2, 16);
-        k3 += __shfl_xor_sync(0xffffffffu, k3, 16);
-        c0 += __shfl_xor_sync(0xffffffffu, c0, 16);
-        c1 += __shfl_xor_sync(0xffffffffu, c1, 16);
-        c2 += __shfl_xor_sync(0xffffffffu, c2, 16);
-        if (on) {
-            const uint32_t id = __float_as_uint(me.z);
-            float4* acc = grad_acc + 3 * (size_t)id;
-            if (qh == 0) {      // lower half of the warp: mean moments + two conic moments
-                if (m0 != 0.f || m1 != 0.f || k0 != 0.f || k1 != 0.f) atomicAdd(acc, make_float4(m0, m1, k0, k1));
-            } else {            // upper half: third conic moment, opacity moment, colour
-                if (k2 != 0.f || k3 != 0.f || c0 != 0.f || c1 != 0.f) atomicAdd(acc + 1, make_float4(k2, k3, c0, c1));
-                if (c2 != 0.f) atomicAdd(reinterpret_cast<float*>(acc + 2), c2);
-            }
-        }
-        __syncwarp();
-    };
-
-    for (int b = 0; b < nbatch; ++b) {
-        ring_wait_full(ring, b, kBwdWarps + 1 /* never "all done" in the backward */);
-        const int s = b % STAGES;
-        const int end = hi - b * kBwdChunk;
-        const int n = min(kBwdChunk, end);
-        const int start = end - n;
-        if (start < wmax) {
-            const float4* __restrict__ SA = ring.A[s];
-            const float4* __restrict__ SB = ring.B[s];
-            const float4* __restrict__ SC = ring.C[s];
-            for (int base = ((n - 1) >> 5) << 5; base >= 0; base -= 32) {
-                if (start + base >= wmax) continue;
-                const int my = base + lane;
-                bool hit = false;
-                if (my < n && start + my < wmax) {
-                    const float4 a = SA[my];
-                    hit = (a.x >= wx0 - a.z) && (a.x <= wx1 + a.z) && (a.y >= wy0 - a.w) && (a.y <= wy1 + a.w);
-                }
-                unsigned m = __ballot_sync(0xffffffffu, hit);
-                while (m) {
-                    const int bit = 31 - __clz(m);             // back to front: deepest surviving entry first
-                    m &= ~(1u << bit);
-                    const int j = base + bit;
-                    const float2 xy = *reinterpret_cast<const float2*>(&SA[j]);
-                    const float4 q = SB[j];
-                    const float4 c = SC[j];
-                    const float dx = xy.x - pixfx, dy = xy.y - pixfy;
-                    const float p = fmaf(q.z * dy, dy, fmaf(q.x, dx, q.y * dy) * dx);   // log2e * power
-                    const float G = ex2_approx(p);
-                    const float alpha = fminf(0.99f, q.w * G);
-                    const bool active = (start + j) < last_contributor && !(p > 0.0f) && !(alpha < 1.0f / 255.0f);
-                    if (!__any_sync(0xffffffffu, active)) continue;
-                    // inactive pairs are replayed with G = 0 (see the header): alpha_e = 0, inv1ma = 1, s = w = 0
-                    const float Ge = active ? G : 0.0f;
-                    const float alpha_e = fminf(0.99f, q.w * Ge);
-                    float inv1ma;                                 // 1 - alpha >= 0.01: MUFU.RCP (1 ulp) without the slow path
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1ma) : "f"(1.0f - alpha_e));
-                    T *= inv1ma;
-                    accum0 = fmaf(last_alpha, lastc0 - accum0, accum0);
-                    accum1 = fmaf(last_alpha, lastc1 - accum1, accum1);
-                    accum2 = fmaf(last_alpha, lastc2 - accum2, accum2);
-                    float dL_dalpha = (c.x - accum0) * g0;
-                    dL_dalpha = fmaf(c.y - accum1, g1, dL_dalpha);
-                    dL_dalpha = fmaf(c.z - accum2, g2, dL_dalpha);
-                    dL_dalpha = fmaf(dL_dalpha, T, (-T_final * inv1ma) * bg_dot);
-                    wb.S[slot][lane] = Ge * (q.w * dL_dalpha);
-                    wb.Wt[slot][lane] = alpha_e * T;
-                    if (lane == 0) wb.meta[slot] = make_float4(xy.x, xy.y, c.w, 0.f);
-                    lastc0 = c.x; lastc1 = c.y; lastc2 = c.z;
-                    last_alpha = alpha_e;
-                    if (++slot == kQ) { flush(kQ); slot = 0; }
-                }
-            }
-        }
-        ring_release(ring, b, lane);
-    }
-    if (slot > 0) flush(slot);
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
-// Round-2 variant of the above (default): the survivors of every 32-entry group are first rank-compacted, DEEPEST FIRST,
-// into a per-warp queue (as the forward does front to back), so the replay loop walks fixed shared-memory addresses two
-// survivors per iteration: no find-first-set / mask update / index arithmetic per survivor, and the loads, the conic
-// polynomial and the ex2 of the second survivor are issued before the first one's dependent transmittance / colour chain
-// (the r1 loop had one survivor in flight and ran at 62 % of the issue rate with 32 % of the warp slots occupied).
-// Ring + park buffers + queues exceed the 48 KB static limit, so the kernel takes its shared memory dynamically.
+// The kernel (round 2): the survivors of every 32-entry group are first rank-compacted, DEEPEST FIRST, into a per-warp queue
+// (as the forward does front to back), so the replay loop walks fixed shared-memory addresses two survivors per iteration:
+// no find-first-set / mask update / index arithmetic per survivor, and the loads, the conic polynomial and the ex2 of the
+// second survivor are issued before the first one's dependent transmittance / colour chain (the r1 loop had one survivor in
+// flight).  Ring + park buffers + queues = 51 KB > the 48 KB static limit: dynamic shared memory, 4 CTAs / SM, 8-stage ring
+// (measured at C2: <8 stages,4 CTAs> 251 us, <6,4> 266, <6,5> 254, <10,4> 299; r1's one-survivor loop with scalar REDs 304).
 // ---------------------------------------------------------------------------------------------------------------------
 struct __align__(16) BwdQueue {
     float4 X[34];      // (mean x, mean y, Gaussian id bits, list position bits)
@@ -353,7 +182,7 @@ __global__ void __launch_bounds__((kBwdWarps + 1) * 32, MIN_BLOCKS) render_backw
         __syncwarp();
     };
 
-    // dependent part of one survivor (see the header of render_backward_gm_kernel for the branch-free state update)
+    // dependent part of one survivor (see the header above for the branch-free state update)
     auto chain = [&](const float4& xq, const float4& q, const float4& c, float G, bool active) {
         const float Ge = active ? G : 0.0f;
         const float alpha_e = fminf(0.99f, q.w * Ge);
@@ -444,36 +273,18 @@ static int set_dyn_smem(K kernel, size_t bytes) {
     return GPSG_OK;
 }
 
-template <int STAGES, int BLOCKS>
-static int launch_q(const Camera& cam, BinningState b, ImageState im, const float* dL_dpix, float4* grad_acc, cudaStream_t stream) {
+int launch_render_backward(const Camera& cam, BinningState b, ImageState im, const float* dL_dpix, float4* grad_acc,
+                           cudaStream_t stream) {
+    constexpr int kStages = GPSG_BWD_STAGES, kBlocks = GPSG_BWD_BLOCKS;
     const unsigned grid = 2u * (unsigned)(cam.grid_x * cam.grid_y);
-    auto kern = render_backward_q_kernel<STAGES, BLOCKS>;
-    const size_t smem = sizeof(BwdSmem<STAGES>);
+    auto kern = render_backward_q_kernel<kStages, kBlocks>;
+    const size_t smem = sizeof(BwdSmem<kStages>);
     int rc = set_dyn_smem(kern, smem);
     if (rc) return rc;
     kern<<<grid, (kBwdWarps + 1) * 32, smem, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges, im.tile_order, im.totals,
                                                       im.final_T, im.n_contrib, dL_dpix, grad_acc);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
-}
-
-int launch_render_backward(const Camera& cam, BinningState b, ImageState im, const float* dL_dpix, float4* grad_acc,
-                           cudaStream_t stream) {
-    static const int variant = [] { const char* e = getenv("GPSG_BWD_VARIANT"); return e ? atoi(e) : 0; }();   // TUNING ONLY
-    switch (variant) {
-        case 1: return launch_q<6, 4>(cam, b, im, dL_dpix, grad_acc, stream);
-        case 2: return launch_q<6, 5>(cam, b, im, dL_dpix, grad_acc, stream);
-        case 3: return launch_q<10, 4>(cam, b, im, dL_dpix, grad_acc, stream);
-        case 4: {
-            const unsigned grid = 2u * (unsigned)(cam.grid_x * cam.grid_y);
-            render_backward_gm_kernel<8, 5><<<grid, (kBwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges,
-                                                                                      im.tile_order, im.totals, im.final_T,
-                                                                                      im.n_contrib, dL_dpix, grad_acc);
-            GPSG_LAUNCH_CHECK();
-            return GPSG_OK;
-        }
-        default: return launch_q<8, 4>(cam, b, im, dL_dpix, grad_acc, stream);
-    }
 }
 
 // A.7 + A.8 fused: per Gaussian, (dL/dmean2D, dL/dconic) -> dL/d{mean3D, cov3D, scale, rotation}.
@@ -486,7 +297,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
     float dm[3] = {0.f, 0.f, 0.f}, dsc[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
     float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float dop = 0.f, dm2[2] = {0.f, 0.f};
-    // packed accumulator row of the compositing backward (see render_backward_gm_kernel)
+    // packed accumulator row of the compositing backward (see render_backward_q_kernel)
     const float4 acc0 = grad_acc[3 * (size_t)i], acc1 = grad_acc[3 * (size_t)i + 1];
     const float dcol[3] = {acc1.z, acc1.w, reinterpret_cast<const float*>(grad_acc + 3 * (size_t)i + 2)[0]};
     if (radii[i] > 0) {

@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256, BIG ? 1 : 4) tile_sort_gather_kernel(cons
             typename TileSort<4>::Smem t4;
             typename TileSort<8>::Smem t8;
         } temp;
-        const uint32_t tile = blockIdx.x;
+        const uint32_t tile = im.tile_order[blockIdx.x];       // longest lists first: the ~2.4 waves of very unequal CTAs pack better
         const uint2 range = im.ranges[tile];
         const int n = (int)(range.y - range.x);
         if (n == 0 || n > (int)kBigTile) return;

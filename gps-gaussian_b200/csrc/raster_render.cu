@@ -14,11 +14,42 @@
 //  * the survivors of each 32-entry group are compacted (rank = popc of the ballot below the lane) into a per-warp
 //    shared-memory queue, so the evaluation loop walks fixed addresses, 8 survivors per unrolled iteration, instead of
 //    find-first-set + index arithmetic per survivor (38 -> 27 SASS instructions per survivor, XU pipe 42 % -> 17 %);
+//  * (r2) the queue is pair-interleaved and the conic polynomial / opacity product of TWO survivors of the same pixel run
+//    as packed fp32 (FADD2 / FMUL2 / FFMA2): 27 -> 21.5 SASS instructions per survivor, bit-identical images;
+//  * (r2) tiles are taken longest list first (tile_order from the tile scan): 122 -> 108 us at C2;
 //  * the conic arrives pre-scaled into the log2 domain, so alpha = o * ex2(p) with p a 5-op polynomial.
 #include "gpsg_internal.cuh"
 #include "slab_ring.cuh"
 
 namespace gpsg {
+
+// ---- packed fp32 (Blackwell `*.f32x2`, SASS FADD2 / FMUL2 / FFMA2): one issue slot does the same IEEE operation on two
+// independent values held in an aligned register pair.  Used across TWO SURVIVORS of the same pixel (their conic polynomials
+// are independent; only the transmittance blend is sequential), so the 8x4 cull block is unchanged -- the r1 attempt packed
+// two PIXELS per lane, which coarsened the culling and lost (profiles/microbench/README.md).
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 
 constexpr int kFwdChunk = 64;   // Gaussians per ring stage (3 x 1 KB)
 constexpr int kFwdStages = 6;   // 6 x 3 KB ring + 5.4 KB of survivor queues = 23.9 KB: still 9 CTAs / SM
@@ -37,9 +68,9 @@ __global__ void __launch_bounds__((kFwdWarps + 1) * 32, 8) render_forward_kernel
     __shared__ SlabRing<kFwdChunk, kFwdStages> ring;
     // per consumer warp: queue of the (at most 32) entries of the current 32-entry group that survive the warp's cull,
     // + 1 pad slot.  Zero-initialised so that a pad / stale slot is always finite data with a defined (non-contributing) result.
-    __shared__ float2 qx[kFwdWarps][34];
-    __shared__ float4 qb[kFwdWarps][33];
-    __shared__ float4 qc[kFwdWarps][33];
+    // PACKED: pair-interleaved queue -- pair p = survivors (2p, 2p+1): QP[k][p] = (xA,xB,yA,yB), (bxA,bxB,byA,byB),
+    // (bzA,bzB,oA,oB), (rA,rB,gA,gB), (bA,bB,posA,posB): every LDS.128 lands two register pairs ready for f32x2 operands.
+    __shared__ float4 qp[kFwdWarps][5][17];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // two CTAs per 16x16 tile; tiles are taken longest list first (tile_order, see tile_scan.cuh)
@@ -50,11 +81,7 @@ __global__ void __launch_bounds__((kFwdWarps + 1) * 32, 8) render_forward_kernel
     const int nbatch = (total + kFwdChunk - 1) / kFwdChunk;
 
     if (tid == 0) ring_init(ring, kFwdWarps);
-    for (int e = tid; e < kFwdWarps * 33; e += (kFwdWarps + 1) * 32) {
-        qx[e / 33][e % 33] = make_float2(0.f, 0.f);
-        qb[e / 33][e % 33] = make_float4(0.f, 0.f, 0.f, 0.f);
-        qc[e / 33][e % 33] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    for (int e = tid; e < kFwdWarps * 5 * 17; e += (kFwdWarps + 1) * 32) (&qp[0][0][0])[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
     if (warp == kFwdWarps) {  // ---------------- producer warp ----------------
@@ -72,9 +99,8 @@ __global__ void __launch_bounds__((kFwdWarps + 1) * 32, 8) render_forward_kernel
     const float pixfx = (float)px, pixfy = (float)py;
     const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
 
-    float2* __restrict__ QX = qx[warp];
-    float4* __restrict__ QB = qb[warp];
-    float4* __restrict__ QC = qc[warp];
+    float4 (*__restrict__ QP)[17] = qp[warp];
+    const unsigned long long pixfx2 = pk2(pixfx, pixfx), pixfy2 = pk2(pixfy, pixfy);
     const unsigned lt_mask = (1u << lane) - 1u;
 
     bool done = !inside;
@@ -109,38 +135,45 @@ __global__ void __launch_bounds__((kFwdWarps + 1) * 32, 8) render_forward_kernel
                     const int cnt = __popc(m);
                     if (hit) {
                         const int r = __popc(m & lt_mask);
-                        float4 c = SC[my];
-                        c.w = __int_as_float(posbase + my);            // list position replaces the id (unused here)
-                        QX[r] = make_float2(a.x, a.y);
-                        QB[r] = SB[my];
-                        QC[r] = c;
+                        const float4 q = SB[my];
+                        const float4 c = SC[my];
+                        float* base = reinterpret_cast<float*>(&QP[0][r >> 1]) + (r & 1);
+                        constexpr int kS = 17 * 4;                      // floats between QP[k] and QP[k+1]
+                        base[0] = a.x;           base[2] = a.y;
+                        base[kS] = q.x;          base[kS + 2] = q.y;
+                        base[2 * kS] = q.z;      base[2 * kS + 2] = q.w;
+                        base[3 * kS] = c.x;      base[3 * kS + 2] = c.y;
+                        base[4 * kS] = c.z;      base[4 * kS + 2] = __int_as_float(posbase + my);
                     }
-                    if (lane == 0) QB[cnt] = make_float4(0.f, 0.f, 0.f, 0.f);   // pad odd counts: opacity 0 never contributes
+                    if (lane == 0 && (cnt & 1)) reinterpret_cast<float*>(&QP[2][cnt >> 1])[3] = 0.f;   // odd count: pad's opacity 0
                     __syncwarp();
 #pragma unroll 4
                     for (int i = 0; i < cnt; i += 2) {
+                        const int pr = i >> 1;
+                        const float4 v0 = QP[0][pr], v1 = QP[1][pr], v2 = QP[2][pr], v3 = QP[3][pr], v4 = QP[4][pr];
+                        const unsigned long long dx2 = sub2(pk2(v0.x, v0.y), pixfx2), dy2 = sub2(pk2(v0.z, v0.w), pixfy2);
+                        // p = log2e * power = bz*dy*dy + (bx*dx + by*dy)*dx, same operation order as the scalar kernel
+                        const unsigned long long t2 = fma2(pk2(v1.x, v1.y), dx2, mul2(pk2(v1.z, v1.w), dy2));
+                        const unsigned long long p2 = fma2(mul2(pk2(v2.x, v2.y), dy2), dy2, mul2(t2, dx2));
+                        float pA, pB;
+                        upk2(p2, pA, pB);
+                        float aA, aB;
+                        upk2(mul2(pk2(v2.z, v2.w), pk2(ex2_approx(pA), ex2_approx(pB))), aA, aB);
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
-                            // Straight-line, predicated evaluation: under SIMT the "contributing" tail runs whenever ANY
-                            // lane contributes (almost always for a survivor), so per-lane branches only add overhead.
-                            const float2 xy = QX[i + u];
-                            const float4 q = QB[i + u];
-                            const float4 c = QC[i + u];
-                            const float dx = xy.x - pixfx, dy = xy.y - pixfy;
-                            // p = log2e * power,  power = -0.5*(cx dx^2 + cz dy^2) - cy dx dy
-                            const float p = fmaf(q.z * dy, dy, fmaf(q.x, dx, q.y * dy) * dx);
-                            const float alpha = fminf(0.99f, q.w * ex2_approx(p));
+                            const float p = u ? pB : pA;
+                            const float alpha = fminf(0.99f, u ? aB : aA);
                             const bool valid = !done && !(p > 0.0f) && !(alpha < 1.0f / 255.0f);
                             const float test_T = T * (1.0f - alpha);
                             const bool stop = valid && (test_T < 0.0001f);
                             const bool upd = valid && !stop;
                             done = done || stop;
                             const float w = upd ? alpha * T : 0.0f;
-                            C0 = fmaf(c.x, w, C0);
-                            C1 = fmaf(c.y, w, C1);
-                            C2 = fmaf(c.z, w, C2);
+                            C0 = fmaf(u ? v3.y : v3.x, w, C0);
+                            C1 = fmaf(u ? v3.w : v3.z, w, C1);
+                            C2 = fmaf(u ? v4.y : v4.x, w, C2);
                             T = upd ? test_T : T;
-                            last_contributor = upd ? __float_as_int(c.w) : last_contributor;
+                            last_contributor = upd ? __float_as_int(u ? v4.w : v4.z) : last_contributor;
                         }
                     }
                     __syncwarp();                                       // queue is rewritten by the next 32 entries
@@ -165,8 +198,8 @@ __global__ void __launch_bounds__((kFwdWarps + 1) * 32, 8) render_forward_kernel
 
 int launch_render_forward(const Camera& cam, BinningState b, ImageState im, float* out_color, cudaStream_t stream) {
     const unsigned grid = 2u * (unsigned)(cam.grid_x * cam.grid_y);
-    render_forward_kernel<<<grid, (kFwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges, im.tile_order, im.totals,
-                                                                    im.final_T, im.n_contrib, out_color);
+    render_forward_kernel<<<grid, (kFwdWarps + 1) * 32, 0, stream>>>(cam, b.slabA, b.slabB, b.slabC, im.ranges, im.tile_order,
+                                                                    im.totals, im.final_T, im.n_contrib, out_color);
     GPSG_LAUNCH_CHECK();
     return GPSG_OK;
 }
