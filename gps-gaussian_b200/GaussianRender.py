@@ -93,6 +93,104 @@ class _RasterizeMaps(torch.autograd.Function):
         return tuple(out)
 
 
+class _RasterizeMapsBatch(torch.autograd.Function):
+    """(settings_list, *12 maps per sample) -> images [B,3,H,W] with ONE host synchronisation for the whole batch: every
+    sample's projection / tile counting is enqueued first (`gpsg_rasterize_forward_maps_begin`), the stream is synchronised
+    once, then every sample is binned, sorted and composited (`..._finish`).  The reference loops over the samples with one
+    synchronisation each (lib/GaussianRender.py:8; upstream reads num_rendered per call).  Per-sample results, saved buffers
+    and the backward are exactly those of `_RasterizeMaps`."""
+
+    @staticmethod
+    def forward(ctx, settings_list, *maps):
+        B = len(settings_list)
+        assert len(maps) == 12 * B
+        dev = maps[1].device
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        stream = torch.cuda.current_stream(dev)
+        sptr = C.c_void_p(stream.cuda_stream)
+        H, W = int(settings_list[0].image_height), int(settings_list[0].image_width)
+        out = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+        totals = torch.zeros((B, 8), dtype=torch.int32).pin_memory()
+        per = []
+        for b in range(B):
+            st = settings_list[b]
+            if int(st.image_height) != H or int(st.image_width) != W:
+                raise RuntimeError("pts2render (gpsg_sm100): all samples of a batch must render at one resolution")
+            vl, xl, il, rl, sl, ol, vr, xr, ir_, rr, sr, orr = maps[12 * b:12 * b + 12]
+            S2 = int(vl.numel())
+            valid = [vl.contiguous().view(torch.uint8), vr.contiguous().view(torch.uint8)]
+            xyz, img = [_f32(xl.detach()), _f32(xr.detach())], [_f32(il.detach()), _f32(ir_.detach())]
+            rot, scale = [_f32(rl.detach()), _f32(rr.detach())], [_f32(sl.detach()), _f32(sr.detach())]
+            opac = [_f32(ol.detach()), _f32(orr.detach())]
+            if valid[1].numel() != S2:
+                raise RuntimeError("pts2render (gpsg_sm100): lmain and rmain pts_valid differ in size")
+            for t, n in ((xyz, 3), (img, 3), (rot, 4), (scale, 3), (opac, 1)):
+                if any(u.numel() != n * S2 for u in t):
+                    raise RuntimeError("pts2render (gpsg_sm100): map shapes do not match pts_valid")
+            if any(u.device != dev for t in (valid, xyz, img, rot, scale, opac) for u in t):
+                raise RuntimeError("pts2render (gpsg_sm100): all source-view maps must live on one CUDA device")
+            radii = torch.empty((2 * S2,), dtype=torch.int32, device=dev)
+            ptrs = (_ptrs(valid), _ptrs(xyz), _ptrs(img), _ptrs(rot), _ptrs(scale), _ptrs(opac))
+            _lib.begin_alloc(dev)
+            try:
+                with torch.cuda.device(dev):
+                    rc = _lib.lib.gpsg_rasterize_forward_maps_begin(
+                        C.byref(st), idx, sptr, S2, *ptrs, C.c_void_p(radii.data_ptr()), _lib.ALLOC_CB, C.c_void_p(1),
+                        _lib.ALLOC_CB, C.c_void_p(3), C.c_void_p(totals[b].data_ptr()))
+            finally:
+                bufs = _lib.end_alloc()
+            _lib.check(rc, "gpsg_rasterize_forward_maps_begin")
+            per.append(dict(S2=S2, tensors=valid + xyz + img + rot + scale + opac, ptrs=ptrs, radii=radii, geom=bufs.get(1),
+                            image=bufs.get(3)))
+        stream.synchronize()                                   # the ONE host synchronisation of the batch
+        ctx.per = []
+        for b in range(B):
+            p = per[b]
+            n = C.c_int32(0)
+            _lib.begin_alloc(dev)
+            try:
+                with torch.cuda.device(dev):
+                    rc = _lib.lib.gpsg_rasterize_forward_maps_finish(
+                        C.byref(settings_list[b]), idx, sptr, p["S2"], *p["ptrs"], C.c_void_p(out[b].data_ptr()),
+                        C.c_void_p(p["radii"].data_ptr()), C.c_void_p(p["geom"].data_ptr()), C.c_void_p(p["image"].data_ptr()),
+                        _lib.ALLOC_CB, C.c_void_p(2), C.c_void_p(totals[b].data_ptr()), C.byref(n))
+            finally:
+                bufs = _lib.end_alloc()
+            _lib.check(rc, "gpsg_rasterize_forward_maps_finish")
+            ctx.per.append(dict(S2=p["S2"], n=int(n.value), tensors=p["tensors"], radii=p["radii"],
+                                bufs=(p["geom"], bufs.get(2), p["image"])))
+        ctx.settings_list, ctx.idx = settings_list, idx
+        ctx.shapes = [tuple(m.shape) for m in maps]
+        ctx._totals = totals                                   # keep the pinned words alive until the copies have landed
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        grads = [None]
+        dev = grad_out.device
+        for b, p in enumerate(ctx.per):
+            t = p["tensors"]
+            valid, xyz, img, rot, scale, opac = t[0:2], t[2:4], t[4:6], t[6:8], t[8:10], t[10:12]
+            new = lambda ref: [torch.empty_like(ref[0]), torch.empty_like(ref[1])]
+            dxyz, dimg, drot, dscale, dopac = new(xyz), new(img), new(rot), new(scale), new(opac)
+            ws = torch.empty(int(_lib.lib.gpsg_rasterize_backward_maps_workspace_bytes(p["S2"])), dtype=torch.uint8, device=dev)
+            g = _f32(grad_out[b].detach())
+            geom, binning, image = p["bufs"]
+            with torch.cuda.device(dev):
+                rc = _lib.lib.gpsg_rasterize_backward_maps(
+                    C.byref(ctx.settings_list[b]), ctx.idx, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream), p["S2"],
+                    p["n"], _ptrs(valid), _ptrs(xyz), _ptrs(img), _ptrs(rot), _ptrs(scale), _ptrs(opac),
+                    C.c_void_p(p["radii"].data_ptr()), C.c_void_p(geom.data_ptr()), C.c_void_p(binning.data_ptr()),
+                    C.c_void_p(image.data_ptr()), C.c_void_p(g.data_ptr()), _ptrs(dxyz), _ptrs(dimg), _ptrs(drot),
+                    _ptrs(dscale), _ptrs(dopac), C.c_void_p(ws.data_ptr()))
+            _lib.check(rc, "gpsg_rasterize_backward_maps")
+            sh = ctx.shapes[12 * b:12 * b + 12]
+            grads += [None, dxyz[0].view(sh[1]), dimg[0].view(sh[2]), drot[0].view(sh[3]), dscale[0].view(sh[4]),
+                      dopac[0].view(sh[5]), None, dxyz[1].view(sh[7]), dimg[1].view(sh[8]), drot[1].view(sh[9]),
+                      dscale[1].view(sh[10]), dopac[1].view(sh[11])]
+        return tuple(grads)
+
+
 def _settings(data, idx, bg_color):
     nv = data['novel_view']
     s = _lib.RasterSettings()
@@ -113,15 +211,18 @@ def _settings(data, idx, bg_color):
 
 
 def pts2render(data, bg_color):
+    """Whole batch with one host synchronisation (`_RasterizeMapsBatch`); a batch of one takes the single-sample path."""
     bs = data['lmain']['img'].shape[0]
-    out = []
+    maps, settings = [], []
     for i in range(bs):
-        maps = []
         for view in _VIEWS:
             d = data[view]
             maps += [d['pts_valid'][i], d['xyz'][i], d['img'][i], d['rot_maps'][i], d['scale_maps'][i], d['opacity_maps'][i]]
-        out.append(_RasterizeMaps.apply(_settings(data, i, bg_color), *maps).unsqueeze(0))
-    data['novel_view']['img_pred'] = torch.cat(out, 0)
+        settings.append(_settings(data, i, bg_color))
+    if bs == 1:
+        data['novel_view']['img_pred'] = _RasterizeMaps.apply(settings[0], *maps).unsqueeze(0)
+    else:
+        data['novel_view']['img_pred'] = _RasterizeMapsBatch.apply(settings, *maps)
     return data
 
 

@@ -87,6 +87,12 @@ lib.gpsg_rasterize_forward_maps.argtypes = [C.POINTER(RasterSettings), _i, _vp, 
 lib.gpsg_rasterize_forward_maps_planned.restype = _i
 lib.gpsg_rasterize_forward_maps_planned.argtypes = [C.POINTER(RasterSettings), _i, _vp, _i, _pp, _pp, _pp, _pp, _pp, _pp, _vp, _vp,
                                                     _vp, _vp, _i64, _vp, _vp]
+lib.gpsg_rasterize_forward_maps_begin.restype = _i
+lib.gpsg_rasterize_forward_maps_begin.argtypes = [C.POINTER(RasterSettings), _i, _vp, _i, _pp, _pp, _pp, _pp, _pp, _pp, _vp,
+                                                  ALLOC_FN, _vp, ALLOC_FN, _vp, _vp]
+lib.gpsg_rasterize_forward_maps_finish.restype = _i
+lib.gpsg_rasterize_forward_maps_finish.argtypes = [C.POINTER(RasterSettings), _i, _vp, _i, _pp, _pp, _pp, _pp, _pp, _pp, _vp, _vp,
+                                                   _vp, _vp, ALLOC_FN, _vp, _vp, C.POINTER(C.c_int32)]
 lib.gpsg_rasterize_backward_maps_workspace_bytes.restype = _sz
 lib.gpsg_rasterize_backward_maps_workspace_bytes.argtypes = [_i]
 lib.gpsg_rasterize_backward_maps.restype = _i
@@ -124,7 +130,8 @@ EXPORTED = ["gpsg_last_error", "gpsg_version", "gpsg_rasterize_forward", "gpsg_r
             "gpsg_corr_sampler_forward", "gpsg_corr_sampler_backward", "gpsg_corr_build_pyramid", "gpsg_corr_build_backward",
             "gpsg_corr_lookup_pyramid_forward", "gpsg_corr_lookup_pyramid_backward", "gpsg_raster_geom_bytes",
             "gpsg_raster_binning_bytes", "gpsg_raster_image_bytes", "gpsg_raster_status_ptr",
-            "gpsg_rasterize_forward_planned", "gpsg_rasterize_forward_maps", "gpsg_rasterize_forward_maps_planned", "gpsg_rasterize_backward_maps_workspace_bytes",
+            "gpsg_rasterize_forward_planned", "gpsg_rasterize_forward_maps", "gpsg_rasterize_forward_maps_planned", "gpsg_rasterize_forward_maps_begin", "gpsg_rasterize_forward_maps_finish",
+            "gpsg_rasterize_backward_maps_workspace_bytes",
             "gpsg_rasterize_backward_maps", "gpsg_unproject_forward", "gpsg_unproject_backward", "gpsg_l1_ssim_workspace_bytes", "gpsg_l1_ssim_forward",
             "gpsg_l1_ssim_backward", "gpsg_profile_enable",
             "gpsg_profile_read",

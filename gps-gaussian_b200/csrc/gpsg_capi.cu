@@ -195,14 +195,18 @@ extern "C" {
 GPSG_API const char* gpsg_last_error(void) { return g_err; }
 int gpsg_version(void) { return 100; }
 
-// Shared body of the exact (one host read) forward: `src` says where the Gaussians come from (AoS tensors or maps).
-static int forward_exact(const GpsgRasterSettings* s, int device, cudaStream_t stream, int P, int sh_M, GaussianSrc src,
-                         const float* shs, float* out_color, int32_t* radii, gpsg_alloc_fn geom_alloc, void* geom_user,
-                         gpsg_alloc_fn binning_alloc, void* binning_user, gpsg_alloc_fn image_alloc, void* image_user,
-                         int32_t* num_rendered) {
+// The exact (one host read) forward in two halves, so that a BATCH of samples needs one host synchronisation in total
+// (lib/GaussianRender.py:8 loops over the samples; upstream synchronises once per sample to read num_rendered):
+//   begin  : projection + pairs-per-tile counts + tile ranges; enqueues the copy of the status words (N, longest list, ...)
+//            into `totals_host` (pinned, >= 6 words).  No synchronisation.
+//   finish : (after the caller synchronised the stream once for all samples) sizes the binning buffer from totals_host,
+//            bins, sorts and composites.
+// `src` says where the Gaussians come from (AoS tensors or maps).
+static int forward_exact_begin(const GpsgRasterSettings* s, int device, cudaStream_t stream, int P, const GaussianSrc& src,
+                               int32_t* radii, gpsg_alloc_fn geom_alloc, void* geom_user, gpsg_alloc_fn image_alloc,
+                               void* image_user, uint32_t* totals_host, void** geom_out, void** image_out) {
     GPSG_CUDA(cudaSetDevice(device));
     const Camera cam = make_camera(*s);
-
     const size_t scan_bytes = scan_temp_bytes(P);
     void* geom_base = geom_alloc(geom_user, GeomState::required(P, scan_bytes));
     if (!geom_base) { set_error("geometry allocator returned NULL"); return GPSG_E_ALLOC; }
@@ -210,29 +214,35 @@ static int forward_exact(const GpsgRasterSettings* s, int device, cudaStream_t s
     void* img_base = image_alloc(image_user, ImageState::required(cam.W, cam.H));
     if (!img_base) { set_error("image allocator returned NULL"); return GPSG_E_ALLOC; }
     ImageState im = ImageState::carve(img_base, cam.W, cam.H);
-    const int tiles = cam.grid_x * cam.grid_y;
-
-    // ---- per-Gaussian projection + pairs-per-tile counts, then tile ranges; one host read: (N, max tile count)
-    uint32_t N = 0, max_count = 0;
+    if (geom_out) *geom_out = geom_base;
+    if (image_out) *image_out = img_base;
     int rc = GPSG_OK;
     GPSG_CUDA(cudaMemsetAsync(im.tile_count, 0, (size_t)((char*)(im.totals + 64) - (char*)im.tile_count), stream));
     if (P > 0) {   // projection + pairs-per-tile histogram; its last CTA also scans the histogram into tile ranges
         { StageTimer t(ST_PREPROCESS, stream, 1); rc = launch_preprocess(cam, P, src, radii, g, im, 0u, stream); }
         if (rc) return rc;
+        GPSG_CUDA(cudaMemcpyAsync(totals_host, im.totals, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     } else {
         { StageTimer t(ST_TILE_SCAN, stream, 1); rc = launch_tile_scan(cam, im, 0u, stream); }
         if (rc) return rc;
+        for (int k = 0; k < 6; ++k) totals_host[k] = 0u;
     }
-    if (P > 0) {
-        uint32_t* slot = pinned_slot();
-        GPSG_REQUIRE(slot != nullptr, "cudaHostAlloc failed");
-        GPSG_CUDA(cudaMemcpyAsync(slot, im.totals, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-        GPSG_CUDA(cudaStreamSynchronize(stream));
-        N = slot[0];
-        max_count = slot[1];
-        GPSG_REQUIRE(slot[5] == 0u, "more than 2^31 (tile, Gaussian) pairs: the splats cover (almost) the whole image each -- "
-                                    "degenerate scene (32-bit pair offsets, as in the upstream rasterizer)");
-    }
+    return GPSG_OK;
+}
+
+static int forward_exact_finish(const GpsgRasterSettings* s, int device, cudaStream_t stream, int P, int sh_M, GaussianSrc src,
+                                const float* shs, float* out_color, int32_t* radii, void* geom_base, void* img_base,
+                                gpsg_alloc_fn binning_alloc, void* binning_user, const uint32_t* totals_host,
+                                int32_t* num_rendered) {
+    GPSG_CUDA(cudaSetDevice(device));
+    const Camera cam = make_camera(*s);
+    GeomState g = GeomState::carve(geom_base, P, scan_temp_bytes(P));
+    ImageState im = ImageState::carve(img_base, cam.W, cam.H);
+    const int tiles = cam.grid_x * cam.grid_y;
+    const uint32_t N = totals_host[0], max_count = totals_host[1];
+    GPSG_REQUIRE(totals_host[5] == 0u, "more than 2^31 (tile, Gaussian) pairs: the splats cover (almost) the whole image each -- "
+                                       "degenerate scene (32-bit pair offsets, as in the upstream rasterizer)");
+    int rc = GPSG_OK;
     if (num_rendered) *num_rendered = (int32_t)N;
     if (shs && P > 0) {   // SH -> RGB for the visible Gaussians (kept in the geometry buffer for the backward)
         rc = launch_sh_forward(P, s->sh_degree, sh_M, s->campos, src.means3D, shs, radii, g.rgb, g.clamped, stream);
@@ -268,6 +278,21 @@ static int forward_exact(const GpsgRasterSettings* s, int device, cudaStream_t s
     if (rc) return rc;
     if (s->debug) GPSG_CUDA(cudaStreamSynchronize(stream));
     return GPSG_OK;
+}
+
+static int forward_exact(const GpsgRasterSettings* s, int device, cudaStream_t stream, int P, int sh_M, GaussianSrc src,
+                         const float* shs, float* out_color, int32_t* radii, gpsg_alloc_fn geom_alloc, void* geom_user,
+                         gpsg_alloc_fn binning_alloc, void* binning_user, gpsg_alloc_fn image_alloc, void* image_user,
+                         int32_t* num_rendered) {
+    uint32_t* slot = pinned_slot();      // thread-local pinned words for the one device->host read of this forward
+    GPSG_REQUIRE(slot != nullptr, "cudaHostAlloc failed");
+    void *geom_base = nullptr, *img_base = nullptr;
+    int rc = forward_exact_begin(s, device, stream, P, src, radii, geom_alloc, geom_user, image_alloc, image_user, slot,
+                                 &geom_base, &img_base);
+    if (rc) return rc;
+    if (P > 0) GPSG_CUDA(cudaStreamSynchronize(stream));
+    return forward_exact_finish(s, device, stream, P, sh_M, src, shs, out_color, radii, geom_base, img_base, binning_alloc,
+                                binning_user, slot, num_rendered);
 }
 
 int gpsg_rasterize_forward(const GpsgRasterSettings* s, int device, void* stream_, int P, int sh_M,
@@ -334,6 +359,36 @@ int gpsg_rasterize_forward_maps(const GpsgRasterSettings* s, int device, void* s
     return forward_exact(s, device, (cudaStream_t)stream_, 2 * pixels_per_view, 0,
                          maps_src(pixels_per_view, valid, xyz, img, rot, scale, opacity), nullptr, out_color, radii,
                          geom_alloc, geom_user, binning_alloc, binning_user, image_alloc, image_user, num_rendered);
+}
+
+int gpsg_rasterize_forward_maps_begin(const GpsgRasterSettings* s, int device, void* stream_, int pixels_per_view,
+                                      const uint8_t* const* valid, const float* const* xyz, const float* const* img,
+                                      const float* const* rot, const float* const* scale, const float* const* opacity,
+                                      int32_t* radii, gpsg_alloc_fn geom_alloc, void* geom_user, gpsg_alloc_fn image_alloc,
+                                      void* image_user, uint32_t* totals_host) {
+    GPSG_REQUIRE(s != nullptr, "settings is NULL");
+    GPSG_REQUIRE(s->image_width > 0 && s->image_height > 0, "image size must be positive");
+    GPSG_REQUIRE(radii && geom_alloc && image_alloc && totals_host, "radii / allocator / totals_host is NULL");
+    int rc = check_maps(pixels_per_view, valid, xyz, img, rot, scale, opacity);
+    if (rc) return rc;
+    return forward_exact_begin(s, device, (cudaStream_t)stream_, 2 * pixels_per_view,
+                               maps_src(pixels_per_view, valid, xyz, img, rot, scale, opacity), radii, geom_alloc, geom_user,
+                               image_alloc, image_user, totals_host, nullptr, nullptr);
+}
+
+int gpsg_rasterize_forward_maps_finish(const GpsgRasterSettings* s, int device, void* stream_, int pixels_per_view,
+                                       const uint8_t* const* valid, const float* const* xyz, const float* const* img,
+                                       const float* const* rot, const float* const* scale, const float* const* opacity,
+                                       float* out_color, int32_t* radii, void* geom_buffer, void* image_buffer,
+                                       gpsg_alloc_fn binning_alloc, void* binning_user, const uint32_t* totals_host,
+                                       int32_t* num_rendered) {
+    GPSG_REQUIRE(s != nullptr, "settings is NULL");
+    GPSG_REQUIRE(out_color && radii && geom_buffer && image_buffer && binning_alloc && totals_host, "a required pointer is NULL");
+    int rc = check_maps(pixels_per_view, valid, xyz, img, rot, scale, opacity);
+    if (rc) return rc;
+    return forward_exact_finish(s, device, (cudaStream_t)stream_, 2 * pixels_per_view, 0,
+                                maps_src(pixels_per_view, valid, xyz, img, rot, scale, opacity), nullptr, out_color, radii,
+                                geom_buffer, image_buffer, binning_alloc, binning_user, totals_host, num_rendered);
 }
 
 size_t gpsg_raster_geom_bytes(int P) { return GeomState::required(P > 0 ? P : 0, scan_temp_bytes(P > 0 ? P : 0)); }

@@ -120,6 +120,27 @@ GPSG_API int gpsg_rasterize_forward_maps(const GpsgRasterSettings* settings, int
                                          float* out_color, int32_t* radii, gpsg_alloc_fn geom_alloc, void* geom_user,
                                          gpsg_alloc_fn binning_alloc, void* binning_user, gpsg_alloc_fn image_alloc,
                                          void* image_user, int32_t* num_rendered);
+/* gpsg_rasterize_forward_maps in two halves, for a BATCH of samples with ONE host synchronisation (reference
+ * lib/GaussianRender.py:8 loops over the samples; upstream synchronises once per sample to read num_rendered):
+ *   _begin : projection, pairs-per-tile counts, tile ranges; allocates the geometry and image buffers through the callbacks
+ *            (the caller keeps the pointers they returned) and enqueues a copy of 6 status words into `totals_host`
+ *            (pinned host memory).  Does NOT synchronise.
+ *   ... the caller synchronises `stream` once after the _begin calls of all samples ...
+ *   _finish: sizes and allocates the binning buffer from totals_host, bins, sorts, composites into out_color.
+ * Results are identical to gpsg_rasterize_forward_maps; the saved buffers feed gpsg_rasterize_backward_maps unchanged. */
+GPSG_API int gpsg_rasterize_forward_maps_begin(const GpsgRasterSettings* settings, int device, void* stream, int pixels_per_view,
+                                               const uint8_t* const* valid, const float* const* xyz, const float* const* img,
+                                               const float* const* rot, const float* const* scale,
+                                               const float* const* opacity, int32_t* radii, gpsg_alloc_fn geom_alloc,
+                                               void* geom_user, gpsg_alloc_fn image_alloc, void* image_user,
+                                               uint32_t* totals_host /* >= 6 words, pinned */);
+GPSG_API int gpsg_rasterize_forward_maps_finish(const GpsgRasterSettings* settings, int device, void* stream, int pixels_per_view,
+                                                const uint8_t* const* valid, const float* const* xyz, const float* const* img,
+                                                const float* const* rot, const float* const* scale,
+                                                const float* const* opacity, float* out_color, int32_t* radii,
+                                                void* geom_buffer, void* image_buffer, gpsg_alloc_fn binning_alloc,
+                                                void* binning_user, const uint32_t* totals_host, int32_t* num_rendered);
+
 /* sync-free form of gpsg_rasterize_forward_maps (same contract as gpsg_rasterize_forward_planned; geom buffer sized for
  * P = 2*pixels_per_view): the serving loop of test_view_interp.py:39-47 renders many novel cameras from ONE pair's
  * cached maps without gathering them and without a host sync. */
