@@ -229,6 +229,7 @@ def run_reference_arm(args, rank, world):
 def _corr_section(dev, hbm_peak_gbs):
     """Volume + pyramid build (fp16 tcgen05 kernel / fp16 + fp32 FFMA kernels) and the fused 4-level lookup, CUDA-event timed."""
     import torch
+    from gps_gaussian_b200 import _lib
     from gps_gaussian_b200.corr import CorrBlockFast1D
     B, D, H, W = 2, 192, 128, 128
     gen = torch.Generator(device=dev).manual_seed(1314)
@@ -253,9 +254,9 @@ def _corr_section(dev, hbm_peak_gbs):
     alg = lambda s: 2 * B * D * H * W * s + 1.875 * B * H * W * W * s          # features in, volume + pyramid out
     with torch.no_grad():
         out["build_fp16_tcgen05_ms"] = timed(lambda: CorrBlockFast1D(f16[0], f16[1]))
-        os.environ["GPSG_CORR_BUILD"] = "ffma"
+        _lib.set_corr_build("ffma")
         out["build_fp16_ffma_ms"] = timed(lambda: CorrBlockFast1D(f16[0], f16[1]))
-        os.environ.pop("GPSG_CORR_BUILD")
+        _lib.set_corr_build("tcgen05")
         out["build_fp32_ffma_ms"] = timed(lambda: CorrBlockFast1D(f32[0], f32[1]))
         blk = CorrBlockFast1D(f16[0], f16[1])
         out["lookup_4level_fp16_ms"] = timed(lambda: blk(coords))
@@ -277,9 +278,9 @@ def _corr_section(dev, hbm_peak_gbs):
         v0 = CorrBlockFast1D.corr(fa, fb_).squeeze(3)
         torch.autograd.grad(v0, (fa, fb_), gvol)
     out["build_fwd_bwd_fp16_tcgen05_ms"] = timed(bwd, 20)
-    os.environ["GPSG_CORR_BUILD"] = "ffma"
+    _lib.set_corr_build("ffma")
     out["build_fwd_bwd_fp16_ffma_ms"] = timed(bwd, 20)
-    os.environ.pop("GPSG_CORR_BUILD")
+    _lib.set_corr_build("tcgen05")
     # CPU port beside it (oracle, scalar C, 1 thread) on a bounded sample: 8 of the 128 rows of the same problem
     try:
         from oracle.corr_oracle import CorrOracle

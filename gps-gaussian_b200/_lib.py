@@ -133,7 +133,7 @@ EXPORTED = ["gpsg_last_error", "gpsg_version", "gpsg_rasterize_forward", "gpsg_r
             "gpsg_rasterize_forward_planned", "gpsg_rasterize_forward_maps", "gpsg_rasterize_forward_maps_planned", "gpsg_rasterize_forward_maps_begin", "gpsg_rasterize_forward_maps_finish",
             "gpsg_rasterize_backward_maps_workspace_bytes",
             "gpsg_rasterize_backward_maps", "gpsg_unproject_forward", "gpsg_unproject_backward", "gpsg_l1_ssim_workspace_bytes", "gpsg_l1_ssim_forward",
-            "gpsg_l1_ssim_backward", "gpsg_profile_enable",
+            "gpsg_l1_ssim_backward", "gpsg_set_corr_build", "gpsg_profile_enable",
             "gpsg_profile_read",
             "gpsg_profile_stage_name"]
 
@@ -170,6 +170,15 @@ def end_alloc():
     bufs = _tls.bufs
     _tls.bufs = {}
     return bufs
+
+
+lib.gpsg_set_corr_build.restype = _i
+lib.gpsg_set_corr_build.argtypes = [_i]
+
+
+def set_corr_build(kind="tcgen05"):
+    """'tcgen05' (default: tensor-core kernels for fp16 volumes when the shape fits) or 'ffma'."""
+    check(lib.gpsg_set_corr_build(1 if kind == "ffma" else 0), "gpsg_set_corr_build")
 
 
 def profile_enable(on=True):

@@ -4,10 +4,28 @@
 #include <cuda_fp16.h>
 #include "gpsg_internal.cuh"
 
+#include <atomic>
+
 #include <cstdlib>
 #include <cstring>
 
 namespace gpsg {
+
+// 0 = tcgen05 / TMEM kernels for fp16 volumes when the shape fits (default), 1 = always the FFMA kernels.  Process-wide; set
+// through gpsg_set_corr_build() (tests and bench.py compare the two formulations) -- the environment variable GPSG_CORR_BUILD
+// is only read ONCE, for the initial value (r1 called getenv on every launch).
+static std::atomic<int> g_corr_build_mode{-1};
+int corr_build_mode() {
+    int m = g_corr_build_mode.load(std::memory_order_relaxed);
+    if (m < 0) {
+        const char* e = getenv("GPSG_CORR_BUILD");
+        m = (e && strcmp(e, "ffma") == 0) ? 1 : 0;
+        g_corr_build_mode.store(m, std::memory_order_relaxed);
+    }
+    return m;
+}
+void set_corr_build_mode(int m) { g_corr_build_mode.store(m ? 1 : 0, std::memory_order_relaxed); }
+
 
 template <typename T> __device__ __forceinline__ float ld_f(const T* p);
 template <> __device__ __forceinline__ float ld_f<float>(const float* p) { return *p; }
@@ -213,10 +231,9 @@ __global__ void __launch_bounds__(256) corr_build_kernel(int B, int D, int H, in
 int launch_corr_build(int dtype, int B, int D, int H, int W1, int W2, const void* f1, const void* f2, void* v0, void* v1,
                       void* v2, void* v3, int levels, cudaStream_t stream) {
     if ((int64_t)B * H * W1 * W2 == 0) return GPSG_OK;
-    {   // fp16 (stage-2 AMP) volumes go to the tcgen05 kernel (corr_tc.cu) when the shape fits; GPSG_CORR_BUILD=ffma opts out
+    {   // fp16 (stage-2 AMP) volumes go to the tcgen05 kernel (corr_tc.cu) when the shape fits; gpsg_set_corr_build(1) / GPSG_CORR_BUILD=ffma at start-up opts out
         void* lv[4] = {v0, v1, v2, v3};
-        const char* e = getenv("GPSG_CORR_BUILD");
-        if (!(e && strcmp(e, "ffma") == 0) && corr_build_tc_supported(dtype, D, W1, W2, f1, f2, lv, levels))
+        if (corr_build_mode() == 0 && corr_build_tc_supported(dtype, D, W1, W2, f1, f2, lv, levels))
             return launch_corr_build_tc(B, D, H, W1, W2, f1, f2, v0, v1, v2, v3, levels, stream);
     }
     const float div = sqrtf((float)D);   // the reference divides by torch.sqrt(torch.tensor(D).float())
@@ -414,9 +431,8 @@ __global__ void __launch_bounds__(256) corr_build_bwd_kernel(int D, int H, int N
 int launch_corr_build_bwd(int dtype, int B, int D, int H, int W1, int W2, const void* f1, const void* f2, const void* g,
                           void* df1, void* df2, cudaStream_t stream) {
     if ((int64_t)B * D * H * W1 * W2 == 0) return GPSG_OK;
-    {   // fp16: tcgen05 kernels (corr_tc.cu) when the shape fits; GPSG_CORR_BUILD=ffma opts out
-        const char* e = getenv("GPSG_CORR_BUILD");
-        if (!(e && strcmp(e, "ffma") == 0) && corr_build_bwd_tc_supported(dtype, D, W1, W2, f1, f2, g, df1, df2))
+    {   // fp16: tcgen05 kernels (corr_tc.cu) when the shape fits; gpsg_set_corr_build(1) / GPSG_CORR_BUILD=ffma at start-up opts out
+        if (corr_build_mode() == 0 && corr_build_bwd_tc_supported(dtype, D, W1, W2, f1, f2, g, df1, df2))
             return launch_corr_build_bwd_tc(B, D, H, W1, W2, f1, f2, g, df1, df2, stream);
     }
     const float div = sqrtf((float)D);

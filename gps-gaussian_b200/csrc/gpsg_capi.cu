@@ -711,6 +711,10 @@ int gpsg_l1_ssim_backward(int device, void* stream_, int planes, int H, int W, c
     return launch_l1_ssim_bwd(planes, H, W, img, gt, dmaps, w_l1, w_ssim, grad_loss, dimg, (cudaStream_t)stream_);
 }
 
+int gpsg_set_corr_build(int mode) {
+    set_corr_build_mode(mode);
+    return GPSG_OK;
+}
 int gpsg_profile_enable(int on) {
     g_prof.on = on == 2 ? 2 : (on != 0);
     return GPSG_OK;

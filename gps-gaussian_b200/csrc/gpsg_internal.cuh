@@ -65,10 +65,14 @@ struct GaussianGrads {
 __device__ __forceinline__ bool src_geom(const GaussianSrc& s, int i, float& x, float& y, float& z, float sc[3], float4& q,
                                          float& op) {
     if (s.S2 == 0) {
-        x = s.means3D[3 * i]; y = s.means3D[3 * i + 1]; z = s.means3D[3 * i + 2];
+        const float* m = s.means3D + 3 * (size_t)i;
+        x = m[0]; y = m[1]; z = m[2];
         if (!s.cov3D_precomp) {
-            sc[0] = s.scales[3 * i]; sc[1] = s.scales[3 * i + 1]; sc[2] = s.scales[3 * i + 2];
-            q = make_float4(s.rots[4 * i], s.rots[4 * i + 1], s.rots[4 * i + 2], s.rots[4 * i + 3]);
+            const float* sp = s.scales + 3 * (size_t)i;
+            sc[0] = sp[0]; sc[1] = sp[1]; sc[2] = sp[2];
+            const float* rp = s.rots + 4 * (size_t)i;
+            q = ((reinterpret_cast<uintptr_t>(s.rots) & 15) == 0) ? __ldg(reinterpret_cast<const float4*>(rp))
+                                                                   : make_float4(rp[0], rp[1], rp[2], rp[3]);
         }
         op = s.opacities[i];
         return true;
@@ -178,6 +182,8 @@ int launch_unproject_bwd(int B, int S, const float* depth, const float* mask, in
                          const float* extr, int extr_rows, const float* ref_intr, const float* Tf_x,
                          const float* dL_dxyz, const float* dL_ddepth, float* dL_dflow, cudaStream_t stream);
 // corr.cu
+int corr_build_mode();            // 0 = tcgen05 when possible, 1 = FFMA kernels
+void set_corr_build_mode(int m);
 int launch_corr_fwd(int dtype, int B, int H, int W1, int W2, const void* vol, int64_t sb, int64_t sh, int64_t sw1,
                     const float* coords, int64_t csb, int r, void* out, cudaStream_t stream);
 int launch_corr_bwd(int dtype, int B, int H, int W1, int W2, const float* coords, int64_t csb, const void* gout, int r,

@@ -249,6 +249,9 @@ GPSG_API int gpsg_l1_ssim_backward(int device, void* stream, int planes, int H, 
  * reset), calls[i] and the number of kernel launches[i]; it returns the number of stages (names via
  * gpsg_profile_stage_name) and resets the accumulators.  Process-wide (autograd runs backward nodes on its own thread).  on = 2 counts launches only (no events: nothing is
  * inserted into the streams, for timed regions that should only be counted). */
+/* fp16 correlation-volume build / backward: 0 = tcgen05 + TMEM kernels when the shape fits (default), 1 = FFMA kernels.
+ * Process-wide switch for comparing the two formulations (tests, bench.py); GPSG_CORR_BUILD=ffma sets the initial value. */
+GPSG_API int gpsg_set_corr_build(int mode);
 GPSG_API int gpsg_profile_enable(int on);
 GPSG_API int gpsg_profile_read(float* total_ms, int32_t* calls, int32_t* launches, int capacity);
 GPSG_API const char* gpsg_profile_stage_name(int stage);

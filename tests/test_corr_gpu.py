@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from gps_gaussian_b200 import synth
+from gps_gaussian_b200 import _lib, synth
 from oracle.corr_oracle import CorrOracle
 
 pytestmark = pytest.mark.gpu
@@ -183,11 +183,11 @@ def test_fp16_tcgen05_build_matches_ffma_kernel_and_oracle(shape):
     f1 = torch.randn(B, D, H, W1, device="cuda", generator=gen).half()
     f2 = torch.randn(B, D, H, W2, device="cuda", generator=gen).half()
     tc = [v.clone() for v in CorrBlockFast1D(f1, f2, num_levels=4, radius=4).corr_pyramid]
-    os.environ["GPSG_CORR_BUILD"] = "ffma"
+    _lib.set_corr_build("ffma")
     try:
         ff = [v.clone() for v in CorrBlockFast1D(f1, f2, num_levels=4, radius=4).corr_pyramid]
     finally:
-        os.environ.pop("GPSG_CORR_BUILD")
+        _lib.set_corr_build("tcgen05")
     pyr = CorrOracle("f64").pyramid(f1.float().cpu().numpy(), f2.float().cpu().numpy(), 4)
     for l in range(4):
         a, b = tc[l].squeeze(3).float(), ff[l].squeeze(3).float()
@@ -233,11 +233,11 @@ def test_fp16_tcgen05_build_backward_matches_ffma_kernel_and_fp64(shape):
         return d1, d2
 
     tc = run()
-    os.environ["GPSG_CORR_BUILD"] = "ffma"
+    _lib.set_corr_build("ffma")
     try:
         ff = run()
     finally:
-        os.environ.pop("GPSG_CORR_BUILD")
+        _lib.set_corr_build("tcgen05")
     r1 = torch.einsum("bhxy,bdhy->bdhx", g.double(), f2.double()) / D ** 0.5
     r2 = torch.einsum("bhxy,bdhx->bdhy", g.double(), f1.double()) / D ** 0.5
     for a, b_, ref in ((tc[0], ff[0], r1), (tc[1], ff[1], r2)):
