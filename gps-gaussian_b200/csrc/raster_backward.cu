@@ -50,7 +50,9 @@ struct __align__(16) BwdWarpBuf {
 // no find-first-set / mask update / index arithmetic per survivor, and the loads, the conic polynomial and the ex2 of the
 // second survivor are issued before the first one's dependent transmittance / colour chain (the r1 loop had one survivor in
 // flight).  Ring + park buffers + queues = 51 KB > the 48 KB static limit: dynamic shared memory, 4 CTAs / SM, 8-stage ring
-// (measured at C2: <8 stages,4 CTAs> 251 us, <6,4> 266, <6,5> 254, <10,4> 299; r1's one-survivor loop with scalar REDs 304).
+// (measured at C2: <8 stages,4 CTAs> 251-254 us, <6,4> 266, <6,5> 254, <5,5> 267, <4,5> 280, <3,5> 294, <4,6> 298, <10,4> 299
+// (3 CTAs): depth of the ring -- how far a fast warp may run ahead of the slowest of its CTA -- matters more than a fifth or
+// sixth CTA; r1's one-survivor loop with scalar REDs: 304).
 // ---------------------------------------------------------------------------------------------------------------------
 struct __align__(16) BwdQueue {
     float4 X[34];      // (mean x, mean y, Gaussian id bits, list position bits)
