@@ -17,6 +17,12 @@
 //  * (r2) the queue is pair-interleaved and the conic polynomial / opacity product of TWO survivors of the same pixel run
 //    as packed fp32 (FADD2 / FMUL2 / FFMA2): 27 -> 21.5 SASS instructions per survivor, bit-identical images;
 //  * (r2) tiles are taken longest list first (tile_order from the tile scan): 122 -> 108 us at C2;
+//  * (r2, tried and NOT kept) a persistent grid (148 x 8 CTAs, atomic cursor over tile_order, ONE ring running across tiles
+//    with the producer lane prefetching the next tile's slabs, tile descriptors through a 2-slot mbarrier mailbox) rendered
+//    bit-identical images but was slower: 114.7 us without the saturation early-out, 118.9 us with an early-out + drain
+//    protocol, against 107.2 us for one CTA per half tile.  The start-up chain it removes (~7 % of the stall samples) is
+//    outweighed by what it adds: consumers of the next tile still wait behind the slowest warp of the current one through
+//    the shared ring, every tile costs two more barrier round trips, and the loop-carried state spills at 48 registers.
 //  * the conic arrives pre-scaled into the log2 domain, so alpha = o * ex2(p) with p a 5-op polynomial.
 #include "gpsg_internal.cuh"
 #include "slab_ring.cuh"
