@@ -300,6 +300,36 @@ def _corr_section(dev, hbm_peak_gbs):
                            "lookup_ms_full_extrapolated": t_look * 1e3 * H / hs}
     except Exception as exc:
         out["cpu_port"] = {"error": repr(exc)}
+    # per-KERNEL rooflines of the sampler side (BASELINE.md section 4 bytes; CUDA events around each launch, library-side):
+    # the Python-call wall times above include allocation + ctypes, these do not
+    try:
+        co = coords.clone()
+        vols = [v.detach() for v in blk._vols]
+        grad = torch.randn(B, 36, H, W, device=dev, generator=gen).half()
+        blk_g = CorrBlockFast1D(f16[0].clone().requires_grad_(True), f16[1].clone().requires_grad_(True))
+        _lib.profile_enable(True)
+        _lib.profile_read()
+        n_it = 50
+        for _ in range(n_it):
+            o = blk_g(co)
+            torch.autograd.grad(o, blk_g._vols, grad, retain_graph=False)
+            CorrBlockFast1D(f16[0], f16[1])
+        pr = _lib.profile_read()
+        _lib.profile_enable(False)
+        s2 = 2
+        b_look = 4 * B * H * W * (10 * s2 + 4 + 9 * s2)          # 4 levels x (10 taps + coord + 9 outputs) per pixel
+        b_look_bwd = 4 * B * H * W * (9 * s2 + 4) + sum(v.numel() for v in vols) * s2      # grads in + coord, dense grad volumes out
+        roof = {}
+        for key, name, nbytes in (("corr_forward", "corr_lookup_fwd_kernel (fused 4 levels)", b_look),
+                                  ("corr_backward", "corr_lookup_bwd_kernel (fused 4 levels)", b_look_bwd),
+                                  ("corr_build", "corr_build_tc_kernel (tcgen05)", alg(2))):
+            if pr.get(key, {}).get("calls"):
+                ms = pr[key]["ms"] / pr[key]["calls"]
+                roof[key] = {"kernel": name, "kernel_ms": ms, "algorithmic_bytes_per_launch": nbytes, "achieved_gbps": nbytes / (ms * 1e-3) / 1e9,
+                             "frac_of_measured_hbm": nbytes / (ms * 1e-3) / 1e9 / hbm_peak_gbs, "bound": "hbm (launch-latency at this size)"}
+        out["kernel_rooflines"] = roof
+    except Exception as exc:
+        out["kernel_rooflines"] = {"error": repr(exc)[:200]}
     out["build_fp16_tcgen05_gbps"] = alg(2) / (out["build_fp16_tcgen05_ms"] * 1e-3) / 1e9
     out["build_fp16_tcgen05_hbm_frac"] = out["build_fp16_tcgen05_gbps"] / hbm_peak_gbs
     out["note"] = "wall of the Python call (allocation of the 4 level tensors + 1 launch), CUDA events, back-to-back"
