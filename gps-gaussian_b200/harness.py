@@ -17,7 +17,6 @@ ROOT = os.path.dirname(HERE)
 DROPIN = os.path.join(HERE, "dropin")
 REF_SRC = "/root/reference"
 REF_STAGED = os.path.join(ROOT, "baseline", "_ref")
-_REF_PACKAGES = ("config", "core", "gaussian_renderer", "lib")
 
 
 def stage_reference(force=False):
