@@ -9,7 +9,7 @@ namespace gpsg {
 
 constexpr int kBwdChunk = 64;   // Gaussians per ring stage
 #ifndef GPSG_BWD_STAGES
-#define GPSG_BWD_STAGES 8       // ring depth / CTAs per SM of the default backward kernel (tuning: build.py passes -D overrides)
+#define GPSG_BWD_STAGES 8       // ring depth / CTAs per SM of the backward kernel (compile-time knobs; sweep in the kernel header)
 #endif
 #ifndef GPSG_BWD_BLOCKS
 #define GPSG_BWD_BLOCKS 4

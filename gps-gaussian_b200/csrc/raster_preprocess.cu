@@ -105,8 +105,9 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
         const int my_radius = (int)ceilf(3.0f * sqrtf(rmax(lambda1, lambda2)));
         // Finite inputs give radius >= 2 (lambda >= 0.3).  A NaN covariance (NaN scale / rotation, e.g. an fp16 overflow in
         // the network under AMP) converts to radius 0, and a radius-0 splat still has a 1-tile rectangle: it would be counted
-        // into its tile but skipped by the scatter (radii <= 0), leaving an uninitialised pair in the tile's list.  Upstream has
-        // the same hole (tiles_touched = 1 with radii = 0: duplicateWithKeys skips it, the sorted list keeps garbage).  Cull it.
+        // into its tile but skipped by the scatter (radii <= 0), leaving an uninitialised pair in the tile's list.  By the recalled
+        // spec of SURVEY Appendix A upstream has the same hole (tiles_touched = 1 with radii = 0: duplicateWithKeys skips it, the
+        // sorted list keeps garbage).  Cull it.
         if (my_radius <= 0) break;
         const float px = ((ndcx + 1.0f) * (float)cam.W - 1.0f) * 0.5f;
         const float py = ((ndcy + 1.0f) * (float)cam.H - 1.0f) * 0.5f;
