@@ -124,3 +124,29 @@ def test_c3_harness_builds_the_reference_model_and_batch_on_cpu(tmp_path):
     data, flow_loss, metrics = st.model(data, is_train=True)
     assert tuple(data["lmain"]["xyz"].shape) == (2, 128 * 128, 3) and data["rmain"]["pts_valid"].dtype == torch.bool
     assert bool(torch.isfinite(flow_loss)) and "train_epe" in metrics
+
+
+@needs_ref
+def test_patch_install_and_uninstall_in_process():
+    """`patch.install()` rebinds modules that are ALREADY imported (incl. the `from core.corr import ...` copy held by
+    core.raft_stereo_human); `patch.uninstall()` puts the reference's own objects back."""
+    from gps_gaussian_b200 import harness, patch
+    harness.stage_reference()
+    harness.add_reference_to_path()
+    import core.corr
+    import core.raft_stereo_human
+    import lib.GaussianRender
+    orig = (core.corr.CorrBlockFast1D, core.corr.CorrSampler, core.raft_stereo_human.CorrBlockFast1D, lib.GaussianRender.pts2render)
+    assert all(o.__module__ in ("core.corr", "lib.GaussianRender") for o in orig)
+    patch.install()
+    try:
+        assert patch.active()
+        assert core.corr.CorrBlockFast1D.__module__ == "gps_gaussian_b200.corr"
+        assert core.raft_stereo_human.CorrBlockFast1D is core.corr.CorrBlockFast1D
+        assert lib.GaussianRender.pts2render.__module__ == "gps_gaussian_b200.GaussianRender"
+        patch.install()                                                   # idempotent
+    finally:
+        patch.uninstall()
+    assert not patch.active()
+    assert (core.corr.CorrBlockFast1D, core.corr.CorrSampler, core.raft_stereo_human.CorrBlockFast1D,
+            lib.GaussianRender.pts2render) == orig
