@@ -859,7 +859,10 @@ def main():
         except Exception as exc:
             p2r = {"error": repr(exc)[:300]}
         if not args.no_train:
-            train, roof_b = _train_section(dev, calls, ndup, P, args.steps, V, peak)
+            try:
+                train, roof_b = _train_section(dev, calls, ndup, P, args.steps, V, peak)
+            except Exception as exc:                               # never lose the headline line to an auxiliary measurement
+                train, roof_b = {"error": repr(exc)[:300]}, None
 
     if rank != 0:
         if world > 1:
