@@ -85,6 +85,31 @@ def test_backward_matches_fp64_autograd(res, P, spread, mul):
         assert rel_err(b, a.numpy()) < 1e-6, name                 # 1e-7 eps in 1/(denom^2+1e-7) is the floor
 
 
+def test_backward_matches_fp64_autograd_with_independent_binning():
+    """Same cross-check, but the autograd forward takes its discrete state (tile lists, ranges) from the independent numpy
+    restatement instead of gpsg_oracle.c: the truth the hand-written A.6-A.8 backward is held to then shares nothing with the
+    C oracle (VERDICT r1 missing #6)."""
+    from oracle import raster_independent as ri
+    from oracle.raster_torch64 import render_autograd
+    sc = synth.random_cube_scene(500, 56, spread=0.45, scale_mul=3.0, bg=(0.2, 0.5, 0.7), seed=9)
+    ind = ri.forward_scene(sc)
+    st_ind = dict(W=sc["W"], H=sc["H"], ranges=ind["ranges"], vals=ind["point_list"],
+                  inputs=dict(view=sc["view"], proj=sc["proj"], tanfovx=sc["tanfovx"], tanfovy=sc["tanfovy"], bg=sc["bg"]))
+    T = lambda a: torch.tensor(np.asarray(a, np.float64), requires_grad=True)
+    m, c, op, s, r = T(sc["means3D"]), T(sc["colors"]), T(sc["opacity"]), T(sc["scales"]), T(sc["rots"])
+    img = render_autograd(st_ind, m, c, op, s, r)
+    assert np.abs(img.detach().numpy() - ind["color"]).max() < 1e-12          # torch forward == numpy forward
+    g = np.random.default_rng(2).standard_normal(ind["color"].shape)
+    (img * torch.tensor(g)).sum().backward()
+    o, st = oracle_forward(sc, "f64")
+    assert np.array_equal(st["vals"], ind["point_list"]) and np.abs(st["color"] - ind["color"]).max() < 1e-12
+    gr = o.backward(st, g)
+    for name, a, b in (("means3D", m.grad, gr["dL_dmeans3D"]), ("colors", c.grad, gr["dL_dcolors"]),
+                       ("opacity", op.grad.reshape(-1), gr["dL_dopacity"]), ("scales", s.grad, gr["dL_dscales"]),
+                       ("rots", r.grad, gr["dL_drots"])):
+        assert rel_err(b, a.numpy()) < 1e-6, name
+
+
 def test_f32_and_f64_oracles_agree():
     sc = synth.random_cube_scene(3000, 128, seed=3)
     _, a = oracle_forward(sc, "f32")
